@@ -1,0 +1,912 @@
+// kernels.cuh -- hand-written sm_100a kernels of the VITS2 inference path (fp32 FFMA family).
+//
+// Activation layout: channels-last, packed utterances.  A tensor that the reference holds as
+// [B, C, T] (training/vits2/models.py) lives here as rows[off[b] + t][C]; `len[b]`/`off[b]` are
+// device arrays so that the frame-resolution kernels never need the host to know T_y.
+// Positions outside [0, len) are never written and read as zero, which reproduces both the
+// reference's x_mask multiplications (attentions.py:50,298,301; modules.py:96-108,148-176) and the
+// per-utterance zero padding of the unmasked decoder convs (modules.py:210-225 with x_mask=None).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+namespace vtts {
+
+// ------------------------------------------------------------------------------------------------
+// Generic grouped conv1d-as-GEMM (direct, im2col-free), fp32 FFMA.
+//   y[t*out_mul + out_add][co] = epi( bias[co] + cond[b][co] + sum_{j,ci} w[j][ci][co] * pro(x[t + j*dil - pad][ci]) )
+// Covers every dense contraction of the path: 1x1 convs (attentions.py:156-162, models.py:374-386),
+// FFN convs (attentions.py:294-302), WN in/res-skip layers (modules.py:155-175), conv_pre
+// (models.py:1024), the polyphase branches of ConvTranspose1d (models.py:1027-1028), ResBlock convs
+// (modules.py:210-225), conv_post (models.py:1040).
+// ------------------------------------------------------------------------------------------------
+constexpr int CV_TT = 64;        // time rows per CTA
+constexpr int CV_TC = 64;        // output channels per CTA
+constexpr int CV_CK = 16;        // input channels per k-step
+constexpr int CV_THREADS = 128;  // 16 (time) x 8 (channel groups of 8)
+constexpr int CV_MAXP = 4;       // problems per grouped launch
+constexpr int CV_XR = 4;         // float4 registers per thread for the input-tile prefetch
+
+enum : int { PRO_NONE = 0, PRO_LRELU = 1 };
+enum : int { EPI_RELU = 1, EPI_GATE = 2, EPI_TANH = 4 };
+
+struct ConvP {
+  const float* x;     // input rows
+  const float* w;     // [k][Cin][ldw]
+  const float* bias;  // [ldw]
+  const float* cond;  // per-utterance vector cond[b*cond_ld + co] added before the activation, or null
+  const float* res;   // residual added after alpha scaling (same row indexing as y), or null
+  float* y;
+  int ldx, xoff, ldw, cond_ld, ldr, roff, ldy, yoff;
+  int Cin, Cout, k, dil, pad;
+  int in_extra;       // logical length = len*rmul + in_extra (ReflectionPad1d((1,0)), models.py:1039)
+  int reflect;        // logical input p maps to physical row (p == 0 ? 1 : p - 1)
+  int out_mul, out_add, out_seq_extra;
+  int pro;
+  float slope;
+  int epi;
+  float alpha;
+};
+
+struct ConvBatch {
+  ConvP p[CV_MAXP];
+  int n;
+  int rmul;  // rows per length unit of the input (1, 4, 16 ...)
+  int xw;    // smem row pitch of the input tile (floats), == 2 (mod 8)
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gsrc), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(CV_THREADS)
+conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int pi = blockIdx.z % cb.n;
+  const int b = blockIdx.z / cb.n;
+  const ConvP& P = cb.p[pi];
+  const int co0 = blockIdx.y * CV_TC;
+  if (co0 >= P.Cout) return;
+  const int Lphys = lens[b] * cb.rmul;
+  const int L = Lphys + P.in_extra;
+  const int t0 = blockIdx.x * CV_TT;
+  if (t0 >= L) return;
+  const long in_base = (long)offs[b] * cb.rmul;
+  const long out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
+
+  extern __shared__ __align__(16) float smem[];
+  const int xw = cb.xw;
+  float* Xs = smem;                 // [CK][xw]
+  float* Ws = smem + CV_CK * xw;    // [2][CK][TC]
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;
+  const int ty = tid >> 4;
+  const int k = P.k, dil = P.dil;
+  const int n_pos = CV_TT + (k - 1) * dil;
+  const int nchunks = P.Cin / CV_CK;
+  const int nsteps = nchunks * k;
+
+  float acc[4][8];
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
+
+  float4 xr[CV_XR];
+
+  auto load_x = [&](int c) {
+#pragma unroll
+    for (int e = 0; e < CV_XR; ++e) {
+      const int it = tid + e * CV_THREADS;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (it < n_pos * 4) {
+        const int pos = it >> 2;
+        const int q = (it & 3) * 4;
+        const int p = t0 + pos - P.pad;
+        if (p >= 0 && p < L) {
+          const int pr = P.reflect ? (p == 0 ? 1 : p - 1) : p;
+          v = __ldg(reinterpret_cast<const float4*>(P.x + (in_base + pr) * (long)P.ldx + P.xoff + c * CV_CK + q));
+          if (P.pro == PRO_LRELU) {
+            v.x = v.x > 0.f ? v.x : v.x * P.slope;
+            v.y = v.y > 0.f ? v.y : v.y * P.slope;
+            v.z = v.z > 0.f ? v.z : v.z * P.slope;
+            v.w = v.w > 0.f ? v.w : v.w * P.slope;
+          }
+        }
+      }
+      xr[e] = v;
+    }
+  };
+  auto store_x = [&]() {
+#pragma unroll
+    for (int e = 0; e < CV_XR; ++e) {
+      const int it = tid + e * CV_THREADS;
+      if (it < n_pos * 4) {
+        const int pos = it >> 2;
+        const int q = (it & 3) * 4;
+        Xs[(q + 0) * xw + pos] = xr[e].x;
+        Xs[(q + 1) * xw + pos] = xr[e].y;
+        Xs[(q + 2) * xw + pos] = xr[e].z;
+        Xs[(q + 3) * xw + pos] = xr[e].w;
+      }
+    }
+  };
+  auto issue_w = [&](int s, int buf) {
+    const int c = s / k, j = s - c * k;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int f = tid + e * CV_THREADS;
+      const int r = f >> 4;
+      const int c4 = (f & 15) * 4;
+      const bool ok = (co0 + c4) < P.ldw;
+      const float* src = P.w + ((long)(j * P.Cin + c * CV_CK + r) * P.ldw + (ok ? co0 + c4 : 0));
+      cp_async16(Ws + (buf * CV_CK + r) * CV_TC + c4, src, ok ? 16 : 0);
+    }
+  };
+
+  load_x(0);
+  store_x();
+  issue_w(0, 0);
+  cp_async_commit();
+  int buf = 0;
+  for (int c = 0; c < nchunks; ++c) {
+    if (c + 1 < nchunks) load_x(c + 1);
+    for (int j = 0; j < k; ++j) {
+      const int s = c * k + j;
+      if (s + 1 < nsteps) issue_w(s + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      const float* xs = Xs + tx + j * dil;
+      const float* ws = Ws + buf * CV_CK * CV_TC + ty * 8;
+#pragma unroll
+      for (int ci = 0; ci < CV_CK; ++ci) {
+        float a[4];
+#pragma unroll
+        for (int m = 0; m < 4; ++m) a[m] = xs[ci * xw + 16 * m];
+        const float4 b0 = *reinterpret_cast<const float4*>(ws + ci * CV_TC);
+        const float4 b1 = *reinterpret_cast<const float4*>(ws + ci * CV_TC + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(a[m], bb[n], acc[m][n]);
+      }
+      __syncthreads();
+      buf ^= 1;
+    }
+    if (c + 1 < nchunks) store_x();
+  }
+
+  // ---- epilogue
+  const int co = co0 + ty * 8;
+  if (co >= P.Cout) return;
+  float add[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    float v = 0.f;
+    if (co + n < P.Cout) {
+      v = P.bias[co + n];
+      if (P.cond) v += P.cond[(long)b * P.cond_ld + co + n];
+    }
+    add[n] = v;
+  }
+  const bool gate = (P.epi & EPI_GATE) != 0;
+  const bool aligned = ((P.ldy | P.yoff) & 3) == 0 && (!P.res || ((P.ldr | P.roff) & 3) == 0);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int t = t0 + tx + 16 * m;
+    if (t >= L) continue;
+    const long orow = out_base + (long)t * P.out_mul + P.out_add;
+    float v[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) v[n] = acc[m][n] + add[n];
+    int nout = 8, oc = co;
+    if (gate) {
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const float tt = tanhf(v[2 * n]);
+        const float ss = 1.f / (1.f + expf(-v[2 * n + 1]));
+        v[n] = tt * ss;
+      }
+      nout = 4;
+      oc = co >> 1;
+    }
+    const int climit = gate ? (P.Cout >> 1) : P.Cout;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (n < nout) {
+        float u = v[n];
+        if (P.epi & EPI_RELU) u = fmaxf(u, 0.f);
+        if (P.epi & EPI_TANH) u = tanhf(u);
+        v[n] = u * P.alpha;
+      }
+    }
+    float* yrow = P.y + orow * (long)P.ldy + P.yoff + oc;
+    const float* rrow = P.res ? (P.res + orow * (long)P.ldr + P.roff + oc) : nullptr;
+    if (aligned && (oc + nout) <= climit) {
+      for (int n4 = 0; n4 < nout; n4 += 4) {
+        float4 o = make_float4(v[n4], v[n4 + 1], v[n4 + 2], v[n4 + 3]);
+        if (rrow) {
+          const float4 r = *reinterpret_cast<const float4*>(rrow + n4);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        *reinterpret_cast<float4*>(yrow + n4) = o;
+      }
+    } else {
+      for (int n = 0; n < nout; ++n)
+        if (oc + n < climit) yrow[n] = v[n] + (rrow ? rrow[n] : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-utterance conditioning: g = emb_g[sid] (models.py:1681); out[b][r] = W[r] . g + bias[r] for the
+// stacked rows of spk_emb_linear (attentions.py:53), dp.cond (models.py:60) and every WN cond_layer
+// (modules.py:151-152).
+// ------------------------------------------------------------------------------------------------
+__global__ void cond_kernel(const float* __restrict__ emb_g, const int* __restrict__ sid, const float* __restrict__ W,
+                            const float* __restrict__ bias, float* __restrict__ out, int G, int R, int n_speakers) {
+  extern __shared__ float gs[];
+  const int b = blockIdx.y;
+  int s = sid[b];
+  s = s < 0 ? 0 : (s >= n_speakers ? n_speakers - 1 : s);
+  for (int i = threadIdx.x; i < G; i += blockDim.x) gs[i] = emb_g[(long)s * G + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (r >= R) return;
+  float a = 0.f;
+  for (int i = lane; i < G; i += 32) a = fmaf(W[(long)r * G + i], gs[i], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[(long)b * R + r] = a + bias[r];
+}
+
+// Embedding * sqrt(H) (models.py:318), optional per-utterance vector (cond_layer_idx == 0).
+__global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
+                             const int* __restrict__ lens, const int* __restrict__ offs, int H, float scale,
+                             int n_vocab, const float* __restrict__ vec, int vec_ld) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x;
+  if (t >= lens[b]) return;
+  const long row = offs[b] + t;
+  int id = ids[row];
+  id = id < 0 ? 0 : (id >= n_vocab ? n_vocab - 1 : id);
+  for (int c = threadIdx.x; c < H; c += blockDim.x) {
+    float v = emb[(long)id * H + c] * scale;
+    if (vec) v += vec[(long)b * vec_ld + c];
+    x[row * H + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// out = LayerNorm_C(a + b) * gamma + beta (+ c) (+ vec[b])     (modules.py:29-32; attentions.py:59,63,
+// spk add :52-56; vits2 residual models.py:377).  One warp per row, C <= 256, C % 32 == 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void add_ln_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, const float* __restrict__ cadd, const float* __restrict__ vec,
+                              int vec_ld, float* __restrict__ out, const int* __restrict__ lens, const int* __restrict__ offs, int C) {
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (t >= lens[b]) return;
+  const long row = offs[b] + t;
+  const int per = C >> 5;
+  float v[8];
+  float s = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const int c = lane + 32 * i;
+    float u = a[row * C + c];
+    if (bsrc) u += bsrc[row * C + c];
+    v[i] = u;
+    s += u;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const float d = v[i] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)C + 1e-5f);
+  for (int i = 0; i < per; ++i) {
+    const int c = lane + 32 * i;
+    float u = (v[i] - mean) * rstd * gamma[c] + beta[c];
+    if (cadd) u += cadd[row * C + c];
+    if (vec) u += vec[(long)b * vec_ld + c];
+    out[row * C + c] = u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Windowed relative-position multi-head self-attention (attentions.py:165-196).  The reference's
+// pad/reshape skew tricks (:216-260) reduce to: score[i,j] = q_i.k_j/sqrt(dk) + [|j-i|<=W] q_i.Ek[j-i+W]/sqrt(dk),
+// out_i = sum_j p_ij (v_j + [|j-i|<=W] Ev[j-i+W]).  Keys >= len are skipped: the reference fills them
+// with -1e4 before the softmax (:183), whose exp underflows to exactly 0 in fp32.
+// Online softmax over key tiles of 32; 4 warps x 4 query rows per CTA.
+// ------------------------------------------------------------------------------------------------
+constexpr int AT_QT = 16, AT_KT = 32, AT_THREADS = 128;
+
+template <int DPL>  // dk = 32*DPL
+__global__ void __launch_bounds__(AT_THREADS)
+attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
+            const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
+            const int* __restrict__ offs) {
+  constexpr int DK = 32 * DPL;
+  constexpr int KS = DK + 1;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int len = lens[b];
+  const int q0 = blockIdx.x * AT_QT;
+  if (q0 >= len) return;
+  const long base = offs[b];
+  const int HT = n_heads * DK;
+  const int nrel = 2 * window + 1;
+
+  extern __shared__ float sm[];
+  float* Ks = sm;                         // [KT][KS]
+  float* Vs = Ks + AT_KT * KS;            // [KT][KS]
+  float* Qs = Vs + AT_KT * KS;            // [QT][DK]
+  float* Rv = Qs + AT_QT * DK;            // [nrel][DK]
+  float* QE = Rv + nrel * DK;             // [QT][nrel]
+  float* Ps = QE + AT_QT * nrel;          // [QT][KT]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < AT_QT * DK; i += AT_THREADS) {
+    const int r = i / DK, d = i - r * DK;
+    const int t = q0 + r;
+    Qs[i] = (t < len) ? (qkv[(base + t) * (long)ld + head * DK + d] / sqrtf((float)DK)) : 0.f;
+  }
+  for (int i = tid; i < nrel * DK; i += AT_THREADS) Rv[i] = relv[i];
+  __syncthreads();
+  // q . Ek for the 2W+1 relative offsets
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = warp * 4 + rr;
+    for (int m = 0; m < nrel; ++m) {
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) a = fmaf(Qs[r * DK + lane + 32 * e], relk[m * DK + lane + 32 * e], a);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0) QE[r * nrel + m] = a;
+    }
+  }
+
+  float mrun[4], lrun[4], acc[4][DPL];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    mrun[r] = -INFINITY;
+    lrun[r] = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[r][e] = 0.f;
+  }
+
+  for (int k0 = 0; k0 < len; k0 += AT_KT) {
+    __syncthreads();  // previous tile fully consumed (also orders QE writes before first use)
+    for (int i = tid; i < AT_KT * (DK / 4); i += AT_THREADS) {
+      const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+      const int t = k0 + r;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (t < len) {
+        const float* rowp = qkv + (base + t) * (long)ld + head * DK + d4;
+        kv = *reinterpret_cast<const float4*>(rowp + HT);
+        vv = *reinterpret_cast<const float4*>(rowp + 2 * HT);
+      }
+      float* kd = Ks + r * KS + d4;
+      float* vd = Vs + r * KS + d4;
+      kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+      vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
+    }
+    __syncthreads();
+    const int key = k0 + lane;
+    const bool kvalid = key < len;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < DK; ++d) {
+      const float kd = Ks[lane * KS + d];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) s[r] = fmaf(Qs[(warp * 4 + r) * DK + d], kd, s[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int qi = q0 + warp * 4 + r;
+      const int rel = key - qi + window;
+      if (rel >= 0 && rel < nrel) s[r] += QE[(warp * 4 + r) * nrel + rel];
+      if (!kvalid) s[r] = -INFINITY;
+      float mx = s[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float mnew = fmaxf(mrun[r], mx);
+      const float corr = expf(mrun[r] - mnew);
+      const float p = kvalid ? expf(s[r] - mnew) : 0.f;
+      float ps = p;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      lrun[r] = lrun[r] * corr + ps;
+      mrun[r] = mnew;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[r][e] *= corr;
+      Ps[(warp * 4 + r) * AT_KT + lane] = p;
+    }
+    __syncwarp();
+    const int kmax = min(AT_KT, len - k0);
+    for (int kk = 0; kk < kmax; ++kk) {
+      float vv[DPL];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) vv[e] = Vs[kk * KS + lane + 32 * e];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float p = Ps[(warp * 4 + r) * AT_KT + kk];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, vv[e], acc[r][e]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int qi = q0 + warp * 4 + r;
+      for (int m = 0; m < nrel; ++m) {
+        const int kk = qi + m - window - k0;
+        if (kk >= 0 && kk < kmax) {
+          const float p = Ps[(warp * 4 + r) * AT_KT + kk];
+#pragma unroll
+          for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, Rv[m * DK + lane + 32 * e], acc[r][e]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int qi = q0 + warp * 4 + r;
+    if (qi < len) {
+      const float inv = 1.f / lrun[r];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) out[(base + qi) * (long)ldo + head * DK + lane + 32 * e] = acc[r][e] * inv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// One DDSConv layer (modules.py:96-108): depthwise dilated conv k -> LN -> GELU(erf) -> 1x1 -> LN ->
+// GELU -> + x.  One CTA = 8 positions x all C channels (C == blockDim.x <= 256).
+// ------------------------------------------------------------------------------------------------
+constexpr int DDS_TT = 8;
+
+struct DdsP {
+  const float* x;
+  float* y;
+  const float *sep_w, *sep_b, *ln1g, *ln1b, *pw_w, *pw_b, *ln2g, *ln2b;
+  int C, k, dil, ldw;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, int C, float (&mean)[DDS_TT],
+                                               float (&rstd)[DDS_TT]) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float s[DDS_TT];
+#pragma unroll
+  for (int i = 0; i < DDS_TT; ++i) {
+    s[i] = v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+  }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < DDS_TT; ++i) red[warp * DDS_TT + i] = s[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < DDS_TT; ++i) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += red[w * DDS_TT + i];
+    mean[i] = t / (float)C;
+  }
+#pragma unroll
+  for (int i = 0; i < DDS_TT; ++i) {
+    const float d = v[i] - mean[i];
+    s[i] = d * d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+  }
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < DDS_TT; ++i) red[warp * DDS_TT + i] = s[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < DDS_TT; ++i) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += red[w * DDS_TT + i];
+    rstd[i] = rsqrtf(t / (float)C + 1e-5f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int len = lens[b];
+  const int t0 = blockIdx.x * DDS_TT;
+  if (t0 >= len) return;
+  const long base = offs[b];
+  const int C = P.C, c = threadIdx.x;
+  __shared__ float red[8 * DDS_TT];
+  __shared__ __align__(16) float ys[256 * DDS_TT];  // [ci][tt]
+
+  float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
+  const int half = (P.k - 1) / 2;
+#pragma unroll
+  for (int i = 0; i < DDS_TT; ++i) {
+    float a = P.sep_b[c];
+    for (int j = 0; j < P.k; ++j) {
+      const int t = t0 + i + (j - half) * P.dil;
+      if (t >= 0 && t < len) a = fmaf(P.sep_w[j * C + c], P.x[(base + t) * (long)C + c], a);
+    }
+    v[i] = a;
+  }
+  block_ln_stats(v, red, C, mean, rstd);
+  {
+    const float g = P.ln1g[c], be = P.ln1b[c];
+#pragma unroll
+    for (int i = 0; i < DDS_TT; ++i) ys[c * DDS_TT + i] = gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
+  }
+  __syncthreads();
+  {
+    const float bias = P.pw_b[c];
+#pragma unroll
+    for (int i = 0; i < DDS_TT; ++i) v[i] = bias;
+#pragma unroll 4
+    for (int ci = 0; ci < C; ++ci) {
+      const float w = __ldg(P.pw_w + (long)ci * P.ldw + c);
+      const float4 y0 = *reinterpret_cast<const float4*>(ys + ci * DDS_TT);
+      const float4 y1 = *reinterpret_cast<const float4*>(ys + ci * DDS_TT + 4);
+      v[0] = fmaf(w, y0.x, v[0]); v[1] = fmaf(w, y0.y, v[1]); v[2] = fmaf(w, y0.z, v[2]); v[3] = fmaf(w, y0.w, v[3]);
+      v[4] = fmaf(w, y1.x, v[4]); v[5] = fmaf(w, y1.y, v[5]); v[6] = fmaf(w, y1.z, v[6]); v[7] = fmaf(w, y1.w, v[7]);
+    }
+  }
+  block_ln_stats(v, red, C, mean, rstd);
+  {
+    const float g = P.ln2g[c], be = P.ln2b[c];
+#pragma unroll
+    for (int i = 0; i < DDS_TT; ++i) {
+      const int t = t0 + i;
+      if (t < len) {
+        const long idx = (base + t) * (long)C + c;
+        P.y[idx] = P.x[idx] + gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
+      }
+    }
+  }
+}
+
+// ConvFlow front (modules.py:366-367 + DDSConv's `x = x + g`, :97-98): h = pre_w * x0 + pre_b + cond.
+__global__ void cf_pre_kernel(const float* __restrict__ x0, const float* __restrict__ pre_w, const float* __restrict__ pre_b,
+                              const float* __restrict__ cond, float* __restrict__ h, const int* __restrict__ lens,
+                              const int* __restrict__ offs, int C) {
+  const int b = blockIdx.y, t = blockIdx.x;
+  if (t >= lens[b]) return;
+  const long row = offs[b] + t;
+  const float xv = x0[row];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) h[row * C + c] = fmaf(pre_w[c], xv, pre_b[c]) + cond[row * C + c];
+}
+
+// z = eps * noise_scale_w (models.py:96); eps either supplied ([B][2][ld]) or Philox.
+__device__ __forceinline__ void philox4x32(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+    const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+    ctr[0] = n0; ctr[1] = n1; ctr[2] = n2; ctr[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream, uint32_t a, uint32_t bidx) {
+  uint32_t ctr[4] = {a, bidx, stream, 0x5eedu};
+  philox4x32(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(ctr[0] >> 8) + 0.5f) * (1.f / 16777216.f);
+  const float u2 = ((float)(ctr[1] >> 8) + 0.5f) * (1.f / 16777216.f);
+  return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
+}
+
+__global__ void dp_noise_kernel(const float* __restrict__ eps, int eps_ld, uint64_t seed, float scale, float* __restrict__ za,
+                                float* __restrict__ zb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lens[b]) return;
+  const long row = offs[b] + t;
+  float e0, e1;
+  if (eps) {
+    e0 = eps[((long)b * 2 + 0) * eps_ld + t];
+    e1 = eps[((long)b * 2 + 1) * eps_ld + t];
+  } else {
+    e0 = philox_normal(seed, 1u, (uint32_t)t, (uint32_t)(2 * b));
+    e1 = philox_normal(seed, 1u, (uint32_t)t, (uint32_t)(2 * b + 1));
+  }
+  za[row] = e0 * scale;
+  zb[row] = e1 * scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Inverse rational-quadratic spline with linear tails (transforms.py:55-193, inverse branch) applied to
+// x1 given the 3*nb-1 parameters of one position (modules.py:373-385).  Op order follows the reference
+// (no FMA contraction) because ceil() of the resulting duration must be bit-stable.
+// ------------------------------------------------------------------------------------------------
+constexpr int SPL_MAXB = 16;
+
+__global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, float* __restrict__ x1, int nb, float bound,
+                                      float sqrt_filter, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lens[b]) return;
+  const long row = offs[b] + t;
+  const float x = x1[row];
+  if (!(x >= -bound && x <= bound)) return;  // linear tails: identity (transforms.py:77)
+  const float* hp = h + row * (long)ldh;
+  float cw[SPL_MAXB + 1], ch[SPL_MAXB + 1], dv[SPL_MAXB + 1];
+  const float den = sqrt_filter;  // h / math.sqrt(filter_channels)  (modules.py:373-374)
+  const float coef = (float)(1.0 - 1e-3 * (double)nb);  // python evaluates (1 - min_bin_width*num_bins) in double
+  for (int pass = 0; pass < 2; ++pass) {
+    float* cum = pass == 0 ? cw : ch;
+    float u[SPL_MAXB];
+    float mx = -INFINITY;
+    for (int i = 0; i < nb; ++i) {
+      u[i] = __fdiv_rn(hp[pass * nb + i], den);
+      mx = fmaxf(mx, u[i]);
+    }
+    float s = 0.f;
+    for (int i = 0; i < nb; ++i) {
+      u[i] = expf(__fsub_rn(u[i], mx));
+      s = __fadd_rn(s, u[i]);
+    }
+    float run = 0.f;
+    cum[0] = -bound;
+    for (int i = 0; i < nb; ++i) {
+      const float wi = __fadd_rn(1e-3f, __fmul_rn(coef, __fdiv_rn(u[i], s)));
+      run = __fadd_rn(run, wi);
+      cum[i + 1] = __fadd_rn(__fmul_rn(2.f * bound, run), -bound);
+    }
+    cum[nb] = bound;
+  }
+  const float cst = 0.5397424172369522f;  // log(exp(1 - 1e-3) - 1)  (transforms.py:73)
+  for (int i = 0; i <= nb; ++i) {
+    const float ud = (i == 0 || i == nb) ? cst : hp[2 * nb + i - 1];
+    const float sp = ud > 20.f ? ud : log1pf(expf(ud));
+    dv[i] = __fadd_rn(1e-3f, sp);
+  }
+  int bin = -1;
+  for (int i = 0; i <= nb; ++i) {
+    const float loc = (i == nb) ? __fadd_rn(ch[i], 1e-6f) : ch[i];
+    bin += (x >= loc) ? 1 : 0;
+  }
+  bin = bin < 0 ? 0 : (bin > nb - 1 ? nb - 1 : bin);
+  const float in_cw = cw[bin], in_w = __fsub_rn(cw[bin + 1], cw[bin]);
+  const float in_ch = ch[bin], in_h = __fsub_rn(ch[bin + 1], ch[bin]);
+  const float delta = __fdiv_rn(in_h, in_w);
+  const float d0 = dv[bin], d1 = dv[bin + 1];
+  const float tsum = __fsub_rn(__fadd_rn(d0, d1), __fmul_rn(2.f, delta));
+  const float dx = __fsub_rn(x, in_ch);
+  const float a = __fadd_rn(__fmul_rn(dx, tsum), __fmul_rn(in_h, __fsub_rn(delta, d0)));
+  const float bq = __fsub_rn(__fmul_rn(in_h, d0), __fmul_rn(dx, tsum));
+  const float c = __fmul_rn(-delta, dx);
+  const float disc = __fsub_rn(__fmul_rn(bq, bq), __fmul_rn(__fmul_rn(4.f, a), c));
+  const float root = __fdiv_rn(__fmul_rn(2.f, c), __fsub_rn(-bq, __fsqrt_rn(disc)));
+  x1[row] = __fadd_rn(__fmul_rn(root, in_w), in_cw);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Durations (models.py:1689-1691; modules.py:296 for the ElementwiseAffine inverse):
+//   logw = (z - m) * exp(-logs);  w = exp(logw) * length_scale;  w_ceil = ceil(w);  cum = cumsum(w_ceil)
+// One CTA per utterance; y_len = max(sum, 1).
+// ------------------------------------------------------------------------------------------------
+__global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, float length_scale,
+                                int* __restrict__ wceil, int* __restrict__ cum, int* __restrict__ ylen,
+                                const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int b = blockIdx.x;
+  const int len = lens[b];
+  const long base = offs[b];
+  __shared__ int part[1024];
+  __shared__ int carry;
+  const float m = ea[ea_ch], nlogs = -ea[ea_n + ea_ch];
+  const float es = expf(nlogs);
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int t0 = 0; t0 < len; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    int wc = 0;
+    if (t < len) {
+      const float logw = __fmul_rn(__fsub_rn(z[base + t], m), es);
+      const float w = __fmul_rn(expf(logw), length_scale);
+      float c = ceilf(w);
+      c = fminf(fmaxf(c, 0.f), 1.0e6f);
+      wc = (int)c;
+      wceil[base + t] = wc;
+    }
+    part[threadIdx.x] = wc;
+    __syncthreads();
+    for (int o = 1; o < blockDim.x; o <<= 1) {
+      int add = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+      __syncthreads();
+      part[threadIdx.x] += add;
+      __syncthreads();
+    }
+    if (t < len) cum[base + t] = carry + part[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) ylen[b] = carry < 1 ? 1 : carry;
+}
+
+__global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restrict__ yoff, int B) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int o = 0;
+    for (int b = 0; b < B; ++b) {
+      yoff[b] = o;
+      o += ylen[b];
+    }
+    yoff[B] = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Length regulator + prior sampling (models.py:1692-1700; commons.generate_path commons.py:128-143):
+// frame j takes token idx = #{i : cum_i <= j};  z_p = m_p[idx] + eps * exp(logs_p[idx]) * noise_scale.
+// stats rows hold [m_p | logs_p] (enc_p.proj output, models.py:323-325).
+// ------------------------------------------------------------------------------------------------
+__global__ void sample_prior_kernel(const float* __restrict__ stats, int I, const int* __restrict__ cum,
+                                    const int* __restrict__ tok_len, const int* __restrict__ tok_off,
+                                    const int* __restrict__ frm_len, const int* __restrict__ frm_off,
+                                    const float* __restrict__ eps, int eps_ld, uint64_t seed, float noise_scale,
+                                    float* __restrict__ zp, int* __restrict__ frame_token) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x;
+  if (j >= frm_len[b]) return;
+  const int T = tok_len[b];
+  const int* cb = cum + tok_off[b];
+  int lo = 0, hi = T;  // first i with cum[i] > j
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cb[mid] > j) hi = mid; else lo = mid + 1;
+  }
+  const int idx = lo;
+  const long frow = (long)frm_off[b] + j;
+  if (threadIdx.x == 0 && frame_token) frame_token[frow] = idx;
+  const bool ok = idx < T;
+  const float* srow = stats + ((long)tok_off[b] + (ok ? idx : 0)) * (2 * I);
+  for (int c = threadIdx.x; c < I; c += blockDim.x) {
+    const float m = ok ? srow[c] : 0.f;
+    const float ls = ok ? srow[I + c] : 0.f;
+    const float e = eps ? eps[((long)b * I + c) * eps_ld + j] : philox_normal(seed, 2u, (uint32_t)j, (uint32_t)(b * I + c));
+    zp[frow * I + c] = __fadd_rn(m, __fmul_rn(__fmul_rn(e, expf(ls)), noise_scale));
+  }
+}
+
+// MRF mean (models.py:1030-1036): out = (a + b + c ...) / n over up to 3 resblock outputs.
+__global__ void mrf_mean_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c, int n,
+                                float* __restrict__ out, long total4) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  float4 s = reinterpret_cast<const float4*>(a)[i];
+  if (n > 1) {
+    const float4 u = reinterpret_cast<const float4*>(b2)[i];
+    s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w;
+  }
+  if (n > 2) {
+    const float4 u = reinterpret_cast<const float4*>(c)[i];
+    s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w;
+  }
+  const float d = (float)n;
+  s.x /= d; s.y /= d; s.z /= d; s.w /= d;
+  reinterpret_cast<float4*>(out)[i] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MB-iSTFT tail (models.py:1041-1054): spec = exp(.), phase = pi*sin(.), inverse STFT as a transposed
+// conv with the fixed basis (stft.py:246-262, no window-sum normalisation), PQMF synthesis
+// (pqmf.py:105-116: zero-stuffing x subbands, 63-tap FIR).  One CTA produces TL_M subband samples
+// (= TL_M*subbands output samples) of one utterance.
+//   post rows: per utterance L1 = 16*Ty + 1 frames of `subbands*(n_fft+2)` channels.
+// ------------------------------------------------------------------------------------------------
+constexpr int TL_M = 256;       // subband samples per CTA
+constexpr int TL_THREADS = 256;
+
+__global__ void __launch_bounds__(TL_THREADS)
+istft_pqmf_kernel(const float* __restrict__ post, int ldp, const float* __restrict__ basis, const float* __restrict__ pqmf,
+                  int subbands, int nfft, int hop, int taps, int up_total /* frames -> post rows multiplier */,
+                  const int* __restrict__ frm_len, const int* __restrict__ frm_off, float* __restrict__ wav, long wav_ld,
+                  int packed_out) {
+  const int b = blockIdx.y;
+  const int Ty = frm_len[b];
+  const int L1 = Ty * up_total + 1;            // post-conv frames
+  const int M = (L1 - 1) * hop;                // subband samples after trimming nfft/2 on both sides
+  const int m0 = blockIdx.x * TL_M;
+  if (m0 >= M) return;
+  const int nbins = nfft / 2 + 1;
+  const int cps = 2 * nbins;                   // channels per subband (18)
+  const int halo = (taps - 1) / 2 / subbands + 1;   // subband samples needed on each side (8)
+  const int ms = m0 - halo, me = min(M, m0 + TL_M) + halo;     // y range [ms, me)
+  // frames contributing to y[m]: 4f <= m + nfft/2 < 4f + nfft
+  int f_lo = (ms + nfft / 2 - (nfft - 1));
+  f_lo = f_lo <= 0 ? 0 : (f_lo + hop - 1) / hop;
+  int f_hi = (me - 1 + nfft / 2) / hop;
+  if (f_hi > L1 - 1) f_hi = L1 - 1;
+  const int nf = f_hi - f_lo + 1;
+  extern __shared__ float sm[];
+  float* rec = sm;                                   // [nf][subbands*cps]  (re[0..nbins) | im[0..nbins)) per subband
+  float* ysub = rec + (size_t)(TL_M / 4 + 16) * subbands * cps;   // [subbands][TL_M + 2*halo]
+  const int yw = TL_M + 2 * halo;
+  const long prow0 = (long)frm_off[b] * up_total + b;
+  for (int i = threadIdx.x; i < nf * subbands * nbins; i += TL_THREADS) {
+    const int f = i / (subbands * nbins);
+    const int r = i - f * subbands * nbins;
+    const int k = r / nbins, c = r - k * nbins;
+    const float* pr = post + (prow0 + f_lo + f) * (long)ldp + k * cps;
+    const float mag = expf(pr[c]);
+    const float ph = 3.14159265358979323846f * sinf(pr[nbins + c]);
+    float sn, cs;
+    sincosf(ph, &sn, &cs);
+    rec[(f * subbands + k) * cps + c] = mag * cs;
+    rec[(f * subbands + k) * cps + nbins + c] = mag * sn;
+  }
+  __syncthreads();
+  const float scale = (float)nfft / (float)hop;
+  for (int i = threadIdx.x; i < subbands * (me - ms); i += TL_THREADS) {
+    const int k = i / (me - ms);
+    const int m = ms + (i - k * (me - ms));
+    float a = 0.f;
+    if (m >= 0 && m < M) {
+      const int u = m + nfft / 2;
+      int fa = u - (nfft - 1);
+      fa = fa <= 0 ? 0 : (fa + hop - 1) / hop;
+      int fb = u / hop;
+      if (fb > L1 - 1) fb = L1 - 1;
+      for (int f = fa; f <= fb; ++f) {
+        const float* rr = rec + ((f - f_lo) * subbands + k) * cps;
+        const int pos = u - f * hop;
+        for (int c = 0; c < cps; ++c) a = fmaf(rr[c], basis[c * nfft + pos], a);
+      }
+      a *= scale;
+    }
+    ysub[k * yw + (m - ms)] = a;
+  }
+  __syncthreads();
+  const int ntap = taps;  // 63
+  const int pad = (taps - 1) / 2;
+  const int n0 = m0 * subbands, n1 = min(M, m0 + TL_M) * subbands;
+  float* wout = packed_out ? (wav + (long)frm_off[b] * up_total * hop * subbands) : (wav + (long)b * wav_ld);
+  for (int n = n0 + threadIdx.x; n < n1; n += TL_THREADS) {
+    float a = 0.f;
+    // up[v] = subbands * y[v/subbands] when v % subbands == 0; out[n] = sum_k sum_j h[k][j] * up_k[n + j - pad]
+    const int vlo = n - pad;
+    int j0 = ((-vlo) % subbands + subbands) % subbands;   // first j with (vlo + j) % subbands == 0
+    for (int j = j0; j < ntap; j += subbands) {
+      const int v = vlo + j;
+      if (v < 0) continue;
+      const int m = v / subbands;
+      if (m >= M) break;
+      for (int k = 0; k < subbands; ++k) a = fmaf(pqmf[k * ntap + j], (float)subbands * ysub[k * yw + (m - ms)], a);
+    }
+    wout[n] = a;
+  }
+}
+
+// int64 -> int32 packing of ids, on device (for the *_dev entry points)
+__global__ void pack_ids_kernel(const int64_t* __restrict__ ids, int t_max, int* __restrict__ out, const int* __restrict__ lens,
+                                const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= lens[b]) return;
+  out[offs[b] + t] = (int)ids[(long)b * t_max + t];
+}
+__global__ void cast_sid_kernel(const int64_t* __restrict__ sid, int* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B) out[i] = (int)sid[i];
+}
+
+}  // namespace vtts

@@ -1,0 +1,239 @@
+"""ctypes binding of libvtts.so (include/vtts.h).  No CPU fallback: importing works without a GPU
+(the library only needs libcudart), creating an Engine requires a CUDA device."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_LIB = None
+
+
+class VttsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("vtts error %d: %s" % (code, msg))
+        self.code = code
+
+
+class VttsConfig(C.Structure):
+    _fields_ = [
+        ("n_vocab", C.c_int32), ("n_speakers", C.c_int32), ("gin_channels", C.c_int32),
+        ("inter_channels", C.c_int32), ("hidden_channels", C.c_int32), ("filter_channels", C.c_int32),
+        ("n_heads", C.c_int32), ("n_layers", C.c_int32), ("kernel_size", C.c_int32), ("window_size", C.c_int32),
+        ("spk_cond_encoder", C.c_int32), ("cond_layer_idx", C.c_int32),
+        ("use_transformer_flows", C.c_int32),
+        ("flow_kernel_size", C.c_int32), ("flow_dilation_rate", C.c_int32), ("flow_wn_layers", C.c_int32),
+        ("flow_n_flows", C.c_int32),
+        ("dp_filter_channels", C.c_int32), ("dp_kernel_size", C.c_int32), ("dp_n_flows", C.c_int32),
+        ("dp_num_bins", C.c_int32),
+        ("dp_tail_bound", C.c_float),
+        ("decoder_type", C.c_int32), ("resblock_type", C.c_int32),
+        ("n_resblock_kernels", C.c_int32), ("resblock_kernel_sizes", C.c_int32 * 8),
+        ("n_resblock_dilations", C.c_int32), ("resblock_dilations", (C.c_int32 * 8) * 8),
+        ("n_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
+        ("upsample_initial_channel", C.c_int32),
+        ("subbands", C.c_int32), ("istft_n_fft", C.c_int32), ("istft_hop", C.c_int32),
+        ("precision", C.c_int32),
+    ]
+
+
+EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "vtts_synthesize",
+           "vtts_durations_dev", "vtts_synthesize_dev", "vtts_hop", "vtts_stage_timings",
+           "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read"]
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load_library(build_if_missing=True):
+    """dlopen the in-tree libvtts.so; fails loudly if it is missing and cannot be built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError("libvtts.so is missing: run `python -m vosk_tts_b200.build`")
+        _build.build()
+    lib = C.CDLL(path)
+    vp, i32, i64p, fp = C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_float)
+    lib.vtts_create.argtypes = [C.POINTER(VttsConfig), vp, C.c_size_t, C.c_char_p, i32, i32, C.POINTER(vp)]
+    lib.vtts_create.restype = i32
+    lib.vtts_destroy.argtypes = [vp]
+    lib.vtts_destroy.restype = None
+    lib.vtts_last_error.argtypes = [vp]
+    lib.vtts_last_error.restype = C.c_char_p
+    lib.vtts_durations.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, C.c_uint64, vp, vp]
+    lib.vtts_durations.restype = i32
+    lib.vtts_synthesize.argtypes = [vp, vp, i32, vp, C.c_int64, vp, i32]
+    lib.vtts_synthesize.restype = i32
+    lib.vtts_durations_dev.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, C.c_uint64, vp]
+    lib.vtts_durations_dev.restype = i32
+    lib.vtts_synthesize_dev.argtypes = [vp, vp, i32, vp, C.c_int64]
+    lib.vtts_synthesize_dev.restype = i32
+    lib.vtts_hop.argtypes = [vp]
+    lib.vtts_hop.restype = i32
+    lib.vtts_stage_timings.argtypes = [vp, vp, i32]
+    lib.vtts_stage_timings.restype = i32
+    lib.vtts_kernel_launches.argtypes = [vp]
+    lib.vtts_kernel_launches.restype = C.c_uint64
+    lib.vtts_stream.argtypes = [vp]
+    lib.vtts_stream.restype = vp
+    lib.vtts_microbench.argtypes = [vp, C.c_char_p, i32]
+    lib.vtts_microbench.restype = C.c_float
+    lib.vtts_debug_flags.argtypes = [vp, i32]
+    lib.vtts_debug_flags.restype = i32
+    lib.vtts_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.vtts_debug_read.restype = i32
+    _LIB = lib
+    return lib
+
+
+def make_c_config(cfg, precision=0):
+    c = VttsConfig()
+    for k in ("n_vocab", "n_speakers", "gin_channels", "inter_channels", "hidden_channels", "filter_channels",
+              "n_heads", "n_layers", "kernel_size", "window_size", "cond_layer_idx", "flow_kernel_size",
+              "flow_dilation_rate", "flow_wn_layers", "flow_n_flows", "dp_filter_channels", "dp_kernel_size",
+              "dp_n_flows", "dp_num_bins", "upsample_initial_channel", "subbands"):
+        setattr(c, k, int(cfg[k]))
+    c.spk_cond_encoder = int(bool(cfg["use_spk_conditioned_encoder"]) and cfg["gin_channels"] > 0 and cfg["n_speakers"] > 0)
+    c.use_transformer_flows = int(bool(cfg["use_transformer_flows"]))
+    c.dp_tail_bound = float(cfg["dp_tail_bound"])
+    c.decoder_type = 0 if cfg["decoder"] == "mb_istft" else 1
+    c.resblock_type = 1 if str(cfg["resblock"]) == "1" else 2
+    rk, rd = cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]
+    c.n_resblock_kernels = len(rk)
+    c.n_resblock_dilations = len(rd[0])
+    for j, k in enumerate(rk):
+        c.resblock_kernel_sizes[j] = int(k)
+        assert len(rd[j]) == len(rd[0])
+        for d, v in enumerate(rd[j]):
+            c.resblock_dilations[j][d] = int(v)
+    c.n_upsamples = len(cfg["upsample_rates"])
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        c.upsample_rates[i] = int(u)
+        c.upsample_kernel_sizes[i] = int(k)
+    c.istft_n_fft = int(cfg["gen_istft_n_fft"])
+    c.istft_hop = int(cfg["gen_istft_hop_size"])
+    c.precision = int(precision)
+    return c
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One engine = one GPU.  `blob` may be a numpy float32 array (host) or an (int device_ptr, n_floats) tuple."""
+
+    def __init__(self, cfg, blob, manifest, device=0, precision=0):
+        self.lib = load_library()
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        ccfg = make_c_config(cfg, precision)
+        if isinstance(blob, tuple):
+            ptr, n, on_dev = C.c_void_p(int(blob[0])), int(blob[1]), 1
+        else:
+            blob = np.ascontiguousarray(blob, dtype=np.float32)
+            ptr, n, on_dev = _ptr(blob), blob.size, 0
+        rc = self.lib.vtts_create(C.byref(ccfg), ptr, n, manifest.encode(), on_dev, int(device), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.vtts_last_error(self.h).decode() if self.h else "allocation failed"
+            if self.h:
+                self.lib.vtts_destroy(self.h)
+                self.h = C.c_void_p()
+            raise VttsError(rc, msg)
+        self.hop = self.lib.vtts_hop(self.h)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.vtts_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise VttsError(rc, self.lib.vtts_last_error(self.h).decode())
+
+    # ---- host-buffer path (what the reference-facing session calls)
+    def durations(self, ids, lengths, sid, scales, noise_dp=None, seed=0, want_durations=False):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        if ids.ndim == 1:
+            ids = ids[None, :]
+        B, t_max = ids.shape
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(B)
+        sid = np.ascontiguousarray(sid, dtype=np.int64).reshape(B)
+        scales = np.ascontiguousarray(scales, dtype=np.float32).reshape(3)
+        if noise_dp is not None:
+            noise_dp = np.ascontiguousarray(noise_dp, dtype=np.float32).reshape(B, 2, t_max)
+        y_len = np.zeros(B, np.int64)
+        dur = np.zeros((B, t_max), np.int32) if want_durations else None
+        self._check(self.lib.vtts_durations(self.h, _ptr(ids), _ptr(lengths), _ptr(sid), B, t_max, _ptr(scales),
+                                            _ptr(noise_dp), int(seed), _ptr(y_len), _ptr(dur)))
+        self._B = B
+        return (y_len, dur) if want_durations else y_len
+
+    def synthesize(self, y_lengths, noise_z=None, want_alignment=False):
+        B = self._B
+        max_f = int(np.max(y_lengths))
+        wav = np.zeros((B, max_f * self.hop), np.float32)
+        z_ld = 0
+        if noise_z is not None:
+            noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
+            assert noise_z.ndim == 3 and noise_z.shape[0] == B
+            z_ld = noise_z.shape[2]
+        idx = np.full((B, max_f), -1, np.int32) if want_alignment else None
+        self._check(self.lib.vtts_synthesize(self.h, _ptr(noise_z), z_ld, _ptr(wav), wav.shape[1], _ptr(idx), max_f))
+        return (wav, idx) if want_alignment else wav
+
+    def infer(self, ids, lengths, sid, scales, noise_dp=None, noise_z=None, seed=0):
+        """Both phases.  noise_z may be a callable(max_frames)->[B,C,max_frames] (T_y is data dependent)."""
+        y_len = self.durations(ids, lengths, sid, scales, noise_dp, seed)
+        if callable(noise_z):
+            noise_z = noise_z(int(y_len.max()))
+        wav = self.synthesize(y_len, noise_z)
+        return wav, y_len
+
+    # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr())
+    def durations_dev(self, d_ids, lengths, d_sid, B, t_max, scales, d_noise_dp=0, seed=0):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(B)
+        scales = np.ascontiguousarray(scales, dtype=np.float32).reshape(3)
+        y_len = np.zeros(B, np.int64)
+        self._check(self.lib.vtts_durations_dev(self.h, C.c_void_p(d_ids), _ptr(lengths), C.c_void_p(d_sid), B, t_max,
+                                                _ptr(scales), C.c_void_p(d_noise_dp) if d_noise_dp else None,
+                                                int(seed), _ptr(y_len)))
+        self._B = B
+        return y_len
+
+    def synthesize_dev(self, d_wav, wav_ld, d_noise_z=0, z_ld=0):
+        self._check(self.lib.vtts_synthesize_dev(self.h, C.c_void_p(d_noise_z) if d_noise_z else None, z_ld,
+                                                 C.c_void_p(d_wav), wav_ld))
+
+    def stage_timings(self):
+        ms = np.zeros(8, np.float32)
+        self.lib.vtts_stage_timings(self.h, _ptr(ms), 8)
+        return dict(encoder=float(ms[0]), duration=float(ms[1]), flow=float(ms[2]), decoder=float(ms[3]),
+                    h2d=float(ms[4]), d2h=float(ms[5]))
+
+    def kernel_launches(self):
+        return int(self.lib.vtts_kernel_launches(self.h))
+
+    def stream(self):
+        return int(self.lib.vtts_stream(self.h) or 0)
+
+    def debug_flags(self, flags):
+        self._check(self.lib.vtts_debug_flags(self.h, int(flags)))
+
+    def debug_read(self, name, max_floats=1 << 26):
+        out = np.zeros(max_floats, np.float32)
+        n = C.c_size_t(0)
+        self._check(self.lib.vtts_debug_read(self.h, name.encode(), _ptr(out), max_floats, C.byref(n)))
+        return out[: n.value].copy()

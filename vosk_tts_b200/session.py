@@ -1,0 +1,62 @@
+"""`onnxruntime.InferenceSession`-shaped facade over the CUDA engine.
+
+The reference creates `self.onnx = onnxruntime.InferenceSession(model.onnx)` (vosk_tts/model.py:46) and
+calls `self.model.onnx.run(None, args)[0]` (vosk_tts/synth.py:123-126).  `VitsSession` is assignable to
+`Model.onnx`: `run(None, feeds)` takes the same feeds dict (keys `input`, `input_lengths`, `scales`,
+`sid`; `bert` / `phone_duration_extra` must be None, synth.py:118-119) and returns
+`[float32 [B,1,1,T_wav]]` like the exported graph (onnx_export.py:65-72).
+"""
+import threading
+
+import numpy as np
+
+from . import config as _config
+from . import weights as _weights
+from .engine import Engine
+
+
+class VitsSession:
+    def __init__(self, state_dict=None, cfg=None, device=0, seed=0, packed=None, precision=0):
+        """state_dict: reference checkpoint `['model']` dict (weight_g/weight_v allowed) or already folded.
+        packed: optional (blob, manifest) to skip packing (e.g. received through an NCCL broadcast)."""
+        self.cfg = cfg or _config.DEFAULT_CONFIG
+        if packed is None:
+            folded = _weights.fold_weight_norm(state_dict)
+            packed = _weights.pack(folded, self.cfg)
+        self.engine = Engine(self.cfg, packed[0], packed[1], device=device, precision=precision)
+        self._lock = threading.Lock()
+        self._seed = int(seed)
+        self._calls = 0
+        self.last_y_lengths = None
+        self.last_wav_lengths = None
+
+    # -- onnxruntime-compatible surface ---------------------------------------------------------
+    def get_providers(self):
+        return ["B200VttsExecutionProvider"]
+
+    def run(self, output_names, feeds, noise=None):
+        """feeds as built at vosk_tts/synth.py:113-120.  `noise` (extension): dict(dp=[B,2,T], z=[B,C,>=T_y] or
+        callable(max_frames)) to inject the two random draws; otherwise Philox with a per-call seed."""
+        for k in ("bert", "phone_duration_extra"):
+            if feeds.get(k) is not None:
+                raise ValueError("feed %r is not None: model_type not supported by this engine (VITS2 graph only)" % k)
+        ids = np.asarray(feeds["input"])
+        if ids.ndim != 2:
+            raise ValueError("multistream inputs ([1,5,T]) are not supported by this engine (VITS2 graph only)")
+        lengths = np.asarray(feeds["input_lengths"]).reshape(-1)
+        sid = feeds.get("sid")
+        sid = np.zeros(ids.shape[0], np.int64) if sid is None else np.asarray(sid).reshape(-1)
+        scales = np.asarray(feeds["scales"], dtype=np.float32).reshape(3)
+        with self._lock:
+            self._calls += 1
+            seed = (self._seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
+            dp = z = None
+            if noise is not None:
+                dp, z = noise.get("dp"), noise.get("z")
+            wav, y_len = self.engine.infer(ids, lengths, sid, scales, dp, z, seed)
+            self.last_y_lengths = y_len
+            self.last_wav_lengths = y_len * self.engine.hop
+        return [wav[:, None, None, :]]
+
+    def close(self):
+        self.engine.close()

@@ -34,3 +34,224 @@ def load_checkpoint(path):
     sd = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
     sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
     return fold_weight_norm(sd)
+
+
+# ----------------------------------------------------------------------------------------------
+# Packing: folded state dict -> one fp32 blob + manifest, laid out the way csrc/ consumes it.
+#   generic conv  <name>.w : [k][Cin][ldw]  (ldw = Cout rounded up to 4, zero padded), <name>.b : [ldw]
+#   every tensor starts on a 256-byte boundary.
+# ----------------------------------------------------------------------------------------------
+def _kaiser(M, beta):
+    n = np.arange(M)
+    alpha = (M - 1) / 2.0
+    return np.i0(beta * np.sqrt(np.clip(1 - ((n - alpha) / alpha) ** 2, 0, 1))) / np.i0(beta)
+
+
+def istft_inverse_basis(n_fft, hop):
+    """OnnxSTFT.__init__ (training/vits2/stft.py:191-214): pinv(scale*[Re;Im]FFT(I)[:n/2+1]).T * hann."""
+    scale = n_fft / hop
+    fb = np.fft.fft(np.eye(n_fft))
+    cutoff = n_fft // 2 + 1
+    fb = np.vstack([np.real(fb[:cutoff]), np.imag(fb[:cutoff])])
+    inv = np.linalg.pinv(scale * fb).T.astype(np.float32)          # FloatTensor(...) cast (:199-200)
+    n = np.arange(n_fft)
+    hann = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / n_fft)).astype(np.float32)   # get_window('hann', fftbins=True).float()
+    return (inv * hann[None, :]).astype(np.float32)                # [2*cutoff, n_fft]
+
+
+def pqmf_synthesis_filter(subbands=4, taps=62, cutoff_ratio=0.15, beta=9.0):
+    """PQMF.__init__ (training/vits2/pqmf.py:15-43,63-89): fp32 [subbands, taps+1]."""
+    n = np.arange(taps + 1)
+    omega_c = np.pi * cutoff_ratio
+    with np.errstate(invalid="ignore", divide="ignore"):
+        h_i = np.sin(omega_c * (n - 0.5 * taps)) / (np.pi * (n - 0.5 * taps))
+    h_i[taps // 2] = np.cos(0) * cutoff_ratio
+    h = h_i * _kaiser(taps + 1, beta)
+    hs = np.zeros((subbands, taps + 1))
+    for k in range(subbands):
+        hs[k] = 2 * h * np.cos((2 * k + 1) * (np.pi / (2 * subbands)) * (n - ((taps - 1) / 2))
+                               - (-1) ** k * np.pi / 4)
+    return hs.astype(np.float32)
+
+
+class _Packer:
+    ALIGN = 64  # floats
+
+    def __init__(self):
+        self.chunks = []
+        self.entries = []
+        self.pos = 0
+
+    def add(self, name, arr):
+        a = np.ascontiguousarray(np.asarray(arr, dtype=np.float32)).reshape(-1)
+        pad = (-self.pos) % self.ALIGN
+        if pad:
+            self.chunks.append(np.zeros(pad, np.float32))
+            self.pos += pad
+        self.entries.append((name, self.pos, a.size))
+        self.chunks.append(a)
+        self.pos += a.size
+
+    def conv(self, name, w, b=None, co_perm=None, ci_perm=None):
+        """w: [Co, Ci, k] (Conv1d layout)."""
+        w = np.asarray(w, np.float32)
+        if co_perm is not None:
+            w = w[co_perm]
+            b = None if b is None else np.asarray(b, np.float32)[co_perm]
+        if ci_perm is not None:
+            w = w[:, ci_perm]
+        co, ci, k = w.shape
+        ldw = (co + 3) // 4 * 4
+        wp = np.zeros((k, ci, ldw), np.float32)
+        wp[:, :, :co] = np.transpose(w, (2, 1, 0))
+        bp = np.zeros(ldw, np.float32)
+        if b is not None:
+            bp[:co] = np.asarray(b, np.float32)
+        self.add(name + ".w", wp)
+        self.add(name + ".b", bp)
+
+    def finish(self):
+        blob = np.concatenate(self.chunks) if self.chunks else np.zeros(0, np.float32)
+        manifest = "".join("%s %d %d\n" % e for e in self.entries)
+        return blob, manifest
+
+
+def convt_phases(u, K):
+    """Polyphase split of ConvTranspose1d(k=K, stride=u, padding=(K-u)//2): for phase r the taps
+    (in increasing input position) are kernel columns j_m, and `pad` inputs lie left of t.
+    out[u*t + r] = sum_m x[t - pad + m] * W[:, :, j_m]."""
+    p = (K - u) // 2
+    phases = []
+    for r in range(u):
+        d_min = -((r + p) // u)            # ceil(-(r+p)/u)
+        d_max = (K - 1 - r - p) // u
+        js = [r + p + u * (d_max - m) for m in range(d_max - d_min + 1)]
+        assert all(0 <= j < K for j in js)
+        phases.append((d_max, js))
+    return phases
+
+
+def pack(w, cfg):
+    """w: folded state dict (reference names); returns (blob float32[n], manifest str)."""
+    g = lambda k: w[k].detach().cpu().numpy() if hasattr(w[k], "detach") else np.asarray(w[k])
+    H, I, G = cfg["hidden_channels"], cfg["inter_channels"], cfg["gin_channels"]
+    D = cfg["dp_filter_channels"]
+    P = _Packer()
+
+    def ln(dst, src):
+        P.add(dst + ".g", g(src + ".gamma"))
+        P.add(dst + ".b", g(src + ".beta"))
+
+    def enc_layer(dst, src, i):
+        a = "%s.attn_layers.%d" % (src, i)
+        wq = np.concatenate([g(a + ".conv_q.weight"), g(a + ".conv_k.weight"), g(a + ".conv_v.weight")], 0)
+        bq = np.concatenate([g(a + ".conv_q.bias"), g(a + ".conv_k.bias"), g(a + ".conv_v.bias")], 0)
+        P.conv(dst + ".qkv", wq, bq)
+        P.conv(dst + ".o", g(a + ".conv_o.weight"), g(a + ".conv_o.bias"))
+        P.add(dst + ".relk", g(a + ".emb_rel_k")[0])
+        P.add(dst + ".relv", g(a + ".emb_rel_v")[0])
+        ln(dst + ".ln1", "%s.norm_layers_1.%d" % (src, i))
+        f = "%s.ffn_layers.%d" % (src, i)
+        P.conv(dst + ".ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"))
+        P.conv(dst + ".ffn2", g(f + ".conv_2.weight"), g(f + ".conv_2.bias"))
+        ln(dst + ".ln2", "%s.norm_layers_2.%d" % (src, i))
+
+    def dds(dst, src, n_layers=3):
+        for i in range(n_layers):
+            P.add("%s.%d.sep_w" % (dst, i), np.transpose(g("%s.convs_sep.%d.weight" % (src, i))[:, 0, :], (1, 0)))
+            P.add("%s.%d.sep_b" % (dst, i), g("%s.convs_sep.%d.bias" % (src, i)))
+            ln("%s.%d.ln1" % (dst, i), "%s.norms_1.%d" % (src, i))
+            P.conv("%s.%d.pw" % (dst, i), g("%s.convs_1x1.%d.weight" % (src, i)), g("%s.convs_1x1.%d.bias" % (src, i)))
+            ln("%s.%d.ln2" % (dst, i), "%s.norms_2.%d" % (src, i))
+
+    # ---- speaker table + all per-utterance conditioning projections as one matrix
+    has_g = cfg["n_speakers"] > 0 and G > 0
+    if has_g:
+        P.add("emb_g", g("emb_g.weight"))
+        rows_w, rows_b = [], []
+        if cfg["use_spk_conditioned_encoder"]:
+            rows_w.append(g("enc_p.encoder.spk_emb_linear.weight"))
+            rows_b.append(g("enc_p.encoder.spk_emb_linear.bias"))
+        rows_w.append(g("dp.cond.weight")[:, :, 0])
+        rows_b.append(g("dp.cond.bias"))
+        nl = cfg["flow_wn_layers"]
+        il = np.arange(2 * H).reshape(2, H).T.reshape(-1)     # gate interleave: [t0,s0,t1,s1,...]
+        for f in range(cfg["flow_n_flows"]):
+            cw = g("flow.flows.%d.enc.cond_layer.weight" % (2 * f))[:, :, 0]
+            cb = g("flow.flows.%d.enc.cond_layer.bias" % (2 * f))
+            for i in range(nl):
+                rows_w.append(cw[i * 2 * H:(i + 1) * 2 * H][il])
+                rows_b.append(cb[i * 2 * H:(i + 1) * 2 * H][il])
+        P.add("cond.w", np.concatenate(rows_w, 0))
+        P.add("cond.b", np.concatenate(rows_b, 0))
+
+    # ---- text encoder
+    P.add("enc.emb", g("enc_p.emb.weight"))
+    for i in range(cfg["n_layers"]):
+        enc_layer("enc.%d" % i, "enc_p.encoder", i)
+    P.conv("enc.proj", g("enc_p.proj.weight"), g("enc_p.proj.bias"))
+
+    # ---- stochastic duration predictor
+    P.conv("dp.pre", g("dp.pre.weight"), g("dp.pre.bias"))
+    P.conv("dp.proj", g("dp.proj.weight"), g("dp.proj.bias"))
+    dds("dp.convs", "dp.convs")
+    for n in range(2, cfg["dp_n_flows"] + 1):
+        src = "dp.flows.%d" % (2 * n - 1)
+        P.add("dp.cf%d.pre_w" % n, g(src + ".pre.weight")[:, 0, 0])
+        P.add("dp.cf%d.pre_b" % n, g(src + ".pre.bias"))
+        dds("dp.cf%d.convs" % n, src + ".convs")
+        P.conv("dp.cf%d.proj" % n, g(src + ".proj.weight"), g(src + ".proj.bias"))
+    P.add("dp.ea", np.concatenate([g("dp.flows.0.m").reshape(-1), g("dp.flows.0.logs").reshape(-1)]))
+
+    # ---- flow (reverse); channel flips are folded into the pre/post weights (see csrc/engine.cu)
+    nf = cfg["flow_n_flows"]
+    half = I // 2
+    rev = np.arange(half)[::-1].copy()
+    for f in range(nf):
+        src = "flow.flows.%d" % (2 * f)
+        dst = "flow.%d" % f
+        flipped = ((nf - f) % 2) == 1
+        P.conv(dst + ".pre", g(src + ".pre.weight"), g(src + ".pre.bias"), ci_perm=rev if flipped else None)
+        if cfg["use_transformer_flows"]:
+            enc_layer(dst + ".tr", src + ".pre_transformer", 0)
+        nl = cfg["flow_wn_layers"]
+        il = np.arange(2 * H).reshape(2, H).T.reshape(-1)
+        for i in range(nl):
+            P.conv("%s.in%d" % (dst, i), g("%s.enc.in_layers.%d.weight" % (src, i)),
+                   g("%s.enc.in_layers.%d.bias" % (src, i)), co_perm=il)
+            rw, rb = g("%s.enc.res_skip_layers.%d.weight" % (src, i)), g("%s.enc.res_skip_layers.%d.bias" % (src, i))
+            if i < nl - 1:
+                P.conv("%s.rsx%d" % (dst, i), rw[:H], rb[:H])
+                P.conv("%s.rss%d" % (dst, i), rw[H:], rb[H:])
+            else:
+                P.conv("%s.rss%d" % (dst, i), rw, rb)
+        P.conv(dst + ".post", g(src + ".post.weight"), g(src + ".post.bias"), co_perm=rev if flipped else None)
+
+    # ---- decoder
+    pre_w = g("dec.conv_pre.weight")
+    if nf % 2 == 1:   # odd number of flips leaves the latent channel-reversed: fold into conv_pre
+        pre_w = pre_w[:, ::-1].copy()
+    P.conv("dec.pre", pre_w, g("dec.conv_pre.bias"))
+    nk = len(cfg["resblock_kernel_sizes"])
+    for i, (u, ku) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        wt = g("dec.ups.%d.weight" % i)                      # [Cin, Cout, K]
+        bt = g("dec.ups.%d.bias" % i)
+        for r, (pad, js) in enumerate(convt_phases(u, ku)):
+            wr = np.stack([wt[:, :, j] for j in js], axis=-1)   # [Cin, Cout, ntaps]
+            P.conv("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)), bt)
+        for j in range(nk):
+            n = i * nk + j
+            nd = len(cfg["resblock_dilation_sizes"][j])
+            for d in range(nd):
+                if cfg["resblock"] == "1":
+                    P.conv("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)), g("dec.resblocks.%d.convs1.%d.bias" % (n, d)))
+                    P.conv("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)), g("dec.resblocks.%d.convs2.%d.bias" % (n, d)))
+                else:
+                    P.conv("dec.rb%d.c.%d" % (n, d), g("dec.resblocks.%d.convs.%d.weight" % (n, d)), g("dec.resblocks.%d.convs.%d.bias" % (n, d)))
+    if cfg["decoder"] == "mb_istft":
+        P.conv("dec.post", g("dec.subband_conv_post.weight"), None)
+        P.add("dec.istft", istft_inverse_basis(cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]))
+        P.add("dec.pqmf", pqmf_synthesis_filter(cfg["subbands"]))
+    else:
+        P.conv("dec.post", g("dec.conv_post.weight"), None)
+    return P.finish()
