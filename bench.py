@@ -1,0 +1,276 @@
+#!/usr/bin/env python
+"""bench.py -- audio samples/sec of the VITS2 inference path (BASELINE.json metric) on N B200s.
+
+One "step" = one pass of the hot path (SynthesizerTrn.infer) over one batch: BASELINE.json configs[1], a single
+128-phoneme utterance (tokens = randint(0,62,(128,), seed 0), sid 2, scales [0.8, 1.0, 0.8], fp32), synthetic seeded
+weights of the mb_istft_vits2_multi architecture (no checkpoint exists on the box).  N > 1: one process per GPU,
+each rank synthesises its own copy of the workload (utterances share nothing -> weak scaling, no collective on the
+utterance path; the packed weights are broadcast once from rank 0 over NCCL at init).
+
+  value  : samples/s with inputs resident in HBM (device-pointer C-ABI), CUDA-event timed per step, L2 flushed
+           between steps, max over ranks.
+  e2e    : same metric through the reference-facing call (VitsSession.run with HOST numpy feeds, host->device and
+           device->host copies inside the timed region, wall clock bracketed by synchronisation).
+  --impl reference : the CPU path (oracle restatement of the reference's PyTorch graph, all host threads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR = 22050
+METRIC = "audio samples/sec @22.05kHz, 128-phoneme utterance"
+
+
+def workload(cfg):
+    import torch
+    g = torch.Generator().manual_seed(0)
+    tok = torch.randint(0, cfg["n_vocab"], (1, 128), generator=g).numpy().astype(np.int64)
+    eps_dp = torch.randn(1, 2, 128, generator=g).numpy()
+    eps_z = torch.randn(1, cfg["inter_channels"], 24 * 128 + 8, generator=g).numpy()
+    return dict(tok=tok, lens=np.array([128], np.int64), sid=np.array([2], np.int64),
+                scales=np.array([0.8, 1.0, 0.8], np.float32), eps_dp=eps_dp, eps_z=eps_z)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_reference_run(cfg, wl, steps, warmup):
+    """Times the oracle port of the reference's CPU graph (the only place bench.py executes oracle/)."""
+    import torch
+    from oracle import vits_oracle as vo
+    from vosk_tts_b200 import synthetic, weights
+    w = weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234))
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tok, lens, sid = torch.as_tensor(wl["tok"]), torch.as_tensor(wl["lens"]), torch.as_tensor(wl["sid"])
+    eps_dp, eps_z = torch.as_tensor(wl["eps_dp"]), torch.as_tensor(wl["eps_z"])
+    times, n = [], 0
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            o = vo.infer(w, cfg, tok, lens, sid, wl["scales"], eps_dp, eps_z)
+            wav = o["o"][0, 0].numpy()
+            pcm = np.clip(wav * 32767.0, -32767.0, 32767.0).astype("int16")   # as vosk_tts/synth.py:127-130
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            n = pcm.shape[-1]
+    return n, times, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    from vosk_tts_b200 import config as C
+    cfg = C.DEFAULT_CONFIG
+    wl = workload(cfg)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    conf = {"workload": "BASELINE configs[1]: one 128-phoneme utterance (randint seed 0), sid=2, scales [0.8,1.0,0.8], "
+                        "mb_istft_vits2_multi architecture, seeded synthetic weights", "batch_per_gpu": 1, "phonemes": 128,
+            "parallelism": "replicas (one utterance stream per GPU, weights broadcast once)", "l2": "flushed between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        n, times, cores = cpu_reference_run(cfg, wl, args.steps, min(args.warmup, 3))
+        tot = sum(times)
+        v = n * len(times) / tot
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": len(times),
+                "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic", "config": dict(conf, frames=n // 256),
+                "rtf": (tot / len(times)) / (n / SR),
+                "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                                 "sample": "%d timed runs of the same 128-phoneme utterance, PyTorch-CPU restatement of SynthesizerTrn.infer "
+                                           "(onnxruntime/model.onnx unavailable), incl. float->int16" % len(times)},
+                "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from vosk_tts_b200 import parallel, synthetic, weights
+    from vosk_tts_b200.engine import Engine
+    from vosk_tts_b200.session import VitsSession
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # ---- weights: packed on rank 0, ONE broadcast, engine created from the device blob
+    t0 = time.perf_counter()
+    blob = manifest = None
+    if rank == 0:
+        blob, manifest = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg)
+    bcast_ms = 0.0
+    if world > 1:
+        torch.cuda.synchronize()
+        tb = time.perf_counter()
+        tblob, manifest = parallel.broadcast_packed(blob, manifest, src=0, device="cuda:%d" % local)
+        torch.cuda.synchronize()
+        bcast_ms = (time.perf_counter() - tb) * 1e3
+        eng = Engine(cfg, (tblob.data_ptr(), tblob.numel()), manifest, device=local)
+        del tblob
+    else:
+        eng = Engine(cfg, blob, manifest, device=local)
+    sess = VitsSession.__new__(VitsSession)
+    sess.cfg, sess.engine, sess._lock, sess._seed, sess._calls = cfg, eng, threading.Lock(), 0, 0
+    sess.last_y_lengths = sess.last_wav_lengths = None
+    init_s = time.perf_counter() - t0
+
+    dev = torch.device("cuda", local)
+    d_ids = torch.as_tensor(wl["tok"], device=dev)
+    d_sid = torch.as_tensor(wl["sid"], device=dev)
+    d_eps_dp = torch.as_tensor(wl["eps_dp"], device=dev).contiguous()
+    # frames of this workload (data dependent): one probe call
+    ylen = eng.durations_dev(d_ids.data_ptr(), wl["lens"], d_sid.data_ptr(), 1, 128, wl["scales"], d_eps_dp.data_ptr())
+    Ty = int(ylen[0])
+    hop = eng.hop
+    d_eps_z = torch.as_tensor(wl["eps_z"][:, :, :Ty], device=dev).contiguous()
+    d_wav = torch.zeros(1, Ty * hop, device=dev)
+    eng.synthesize_dev(d_wav.data_ptr(), Ty * hop, d_eps_z.data_ptr(), Ty)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
+
+    def step_dev():
+        yl = eng.durations_dev(d_ids.data_ptr(), wl["lens"], d_sid.data_ptr(), 1, 128, wl["scales"], d_eps_dp.data_ptr())
+        eng.synthesize_dev(d_wav.data_ptr(), Ty * hop, d_eps_z.data_ptr(), Ty)
+        return int(yl[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    launches0 = eng.kernel_launches()
+    eng.profile(True)
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(estream)
+        step_dev()
+        e1.record(estream)
+        e1.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+    barrier()
+    prof = eng.profile_read()
+    eng.profile(False)
+    launches = eng.kernel_launches() - launches0
+    stage = eng.stage_timings()
+    total_ms = float(sum(step_ms))
+    # ---- e2e through the reference-facing call with host buffers
+    feeds = {"input": wl["tok"], "input_lengths": wl["lens"], "scales": wl["scales"], "sid": wl["sid"], "bert": None,
+             "phone_duration_extra": None}
+    noise = {"dp": wl["eps_dp"], "z": (lambda mf: wl["eps_z"][:, :, :mf])}
+    for _ in range(3):
+        sess.run(None, feeds, noise=noise)
+    e2e_t = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        audio = sess.run(None, feeds, noise=noise)[0]
+        e2e_t.append(time.perf_counter() - t1)
+    barrier()
+    clocks = sampler.summary() if sampler else None
+    e2e_total = float(sum(e2e_t))
+    n_samples = Ty * hop
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_total = float(t[0]), float(t[1])
+    if rank == 0:
+        pk = peaks()
+        value = world * n_samples * args.steps / (total_ms / 1e3)
+        e2e_v = world * n_samples * args.steps / e2e_total
+        conv_s = prof["conv_ms"] / 1e3
+        ach = prof["conv_flops"] / conv_s / 1e12 if conv_s > 0 else 0.0
+        # CPU baseline beside it (bounded sample), N=1 only
+        cpu = None
+        if world == 1:
+            n, times, cores = cpu_reference_run(cfg, wl, args.cpu_steps, 2)
+            cpu = {"value": n * len(times) / sum(times), "unit": "samples/s", "cores": cores, "kind": "port",
+                   "sample": "%d runs of the same utterance on the host cores (PyTorch-CPU restatement of the reference graph; "
+                             "onnxruntime unavailable), %.0f ms each" % (len(times), 1e3 * sum(times) / len(times))}
+        line = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "fp32", "data": "synthetic", "config": dict(conf, frames=Ty, samples_per_step=n_samples),
+                "rtf": (total_ms / 1e3 / args.steps) / (n_samples / SR),
+                "e2e": {"value": e2e_v, "unit": "samples/s", "ms_per_step": 1e3 * e2e_total / args.steps,
+                        "h2d_bytes_per_step": int(wl["tok"].nbytes + 16 + 8 + wl["eps_dp"].nbytes + wl["eps_z"][:, :, :Ty].nbytes),
+                        "d2h_bytes_per_step": int(n_samples * 4 + 8)},
+                "gpu_launches": int(launches),
+                "roofline": {"kernel": "conv_kernel (dense conv1d-as-GEMM family, fp32 FFMA)", "bound": "tensor", "achieved": ach,
+                             "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"],
+                             "peak_source": pk["src"] + " cuBLAS bf16 (sustained); this fp32 kernel runs on the FFMA pipe "
+                             "(upper bound 148 SM x 128 lanes x 2 x sm_clock ~ 74.5 TFLOP/s)",
+                             "traffic": None, "launches_per_step": prof["conv_launches"] / max(args.steps, 1),
+                             "share_of_step": prof["conv_ms"] / total_ms if total_ms else None,
+                             "flops_per_step": prof["conv_flops"] / max(args.steps, 1)},
+                "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage,
+                "init": {"seconds": init_s, "weight_broadcast_ms": bcast_ms, "weight_bytes": 4 * int(len(blob))}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

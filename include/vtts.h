@@ -115,6 +115,19 @@ void* vtts_stream(vtts_handle h);
 /* Runs one named kernel micro-benchmark on the engine's device; see csrc/engine.cu. Returns ms or <0. */
 float vtts_microbench(vtts_handle h, const char* what, int iters);
 
+/* CUDA graphs (default on): a call shape (batch, lengths) seen before is captured once and replayed, which removes
+ * the ~160 per-call kernel-launch overheads at batch 1.  vtts_graph_replays counts graph launches so far. */
+int vtts_set_graphs(vtts_handle h, int enable);
+uint64_t vtts_graph_replays(vtts_handle h);
+
+/* Per-launch profiling of the dense-conv kernel family (the dominant kernels): while enabled every launch is
+ * bracketed by CUDA events on the engine's stream.  vtts_profile_read returns the summed device time, the
+ * number of launches and the algorithmic FLOPs (2*Cin*k*Cout per output position) since vtts_profile(h,1). */
+int vtts_profile(vtts_handle h, int enable);
+int vtts_profile_read(vtts_handle h, double* conv_ms, uint64_t* conv_launches, double* conv_flops);
+/* Same counters for the tcgen05 conv kernel (precision mode 1). */
+int vtts_profile_read_tc(vtts_handle h, double* ms, uint64_t* launches, double* flops);
+
 /* Test hooks: flags bit0 keeps a copy of z_p (models.py:1700); vtts_debug_read copies a named workspace
  * tensor of the last call ("x", "stats", "dx", "za", "zb", "condv", "z_p", "z", "d0", "stage<i>", "post") to
  * host memory in the engine's channels-last packed layout. */

@@ -17,7 +17,7 @@ def main():
     sd = synthetic.make_random_checkpoint(cfg, 1234)
     w = weights.fold_weight_norm(sd)
     t0 = time.time(); blob, man = weights.pack(w, cfg); print("pack %.2fs" % (time.time() - t0))
-    eng = Engine(cfg, blob, man, device=0)
+    eng = Engine(cfg, blob, man, device=0, precision=int(os.environ.get('PRECISION', '0')))
     eng.debug_flags(1)
     cases = sys.argv[1:] or ["t17_sid2", "t128_sid2", "t1_single"]
     for name in cases:
@@ -79,11 +79,15 @@ def main():
     # quick timing of the headline case
     g = np.load(os.path.join(ROOT, "tests", "golden", "t128_sid2.npz"))
     tok = g["u0_tokens"]; T = len(tok)
-    for it in range(5):
+    for it in range(8):
+        if it == 5:
+            eng.debug_flags(0)
         t0 = time.perf_counter()
         wav, yl = eng.infer(tok[None], [T], [2], g["scales"], g["u0_eps_dp"][None], g["u0_eps_z"][None])
         dt = time.perf_counter() - t0
-        print("e2e infer %.3f ms, samples %d, %s" % (dt * 1e3, int(yl[0]) * 256, eng.stage_timings()))
+        print("e2e infer %.3f ms, samples %d, %s replays=%d" % (dt * 1e3, int(yl[0]) * 256, eng.stage_timings(), eng.graph_replays()))
+    ref = g["u0_wav"]
+    print("graph-mode wav vs golden", float(np.abs(wav[0, :len(ref)] - ref).max()))
 
 if __name__ == "__main__":
     main()

@@ -1,0 +1,364 @@
+// conv_tc.cuh -- dense conv1d-as-GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   D[t, co] (fp32, TMEM) = sum_{tap j} sum_{ci} A_j[t, ci] * W_j[co, ci]
+//     A_j = rows (t0 + j*dil - pad .. +128) x 64 channels of the producer's *split-bf16 planes* (hi + lo = fp32
+//           value to ~2^-17), K-major, fetched by TMA with the 128-byte swizzle straight from the channels-last
+//           activation buffer (im2col-free: a tap shift is just a different TMA row coordinate; rows outside the
+//           utterance are zero through TMA out-of-bounds fill or the zeroed gap rows between packed utterances),
+//     W_j = 64..128 output channels x 64 input channels of the packed bf16 hi/lo weights of tap j.
+//   Three bf16 MMAs per K16 slice (hi*hi + lo*hi + hi*lo, fp32 accumulate) give fp32-class accuracy (~1e-5 rel)
+//   at 1/3 of the bf16 tensor rate -- about 10x the FFMA pipe -- which keeps the waveform inside the 1e-3 budget
+//   where single-pass bf16 (4.9e-3) or TF32 (6e-4 at 0.2 amplitude) do not (SURVEY.md section 7 "Hard parts").
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias/cond/activation/residual -> fp32 rows and/or split-bf16 planes for the
+// next conv).  A 4-stage mbarrier ring decouples TMA from the tensor pipe.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vtts {
+
+constexpr int TC_BM = 128;        // time rows per CTA (UMMA M)
+constexpr int TC_BK = 64;         // input channels per stage (one 128-byte swizzle atom of bf16)
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_MAXP = 4;
+
+enum : int { TCE_RELU = 1, TCE_GATE = 2 };
+
+struct TcProblem {
+  CUtensorMap a_hi, a_lo, w_hi, w_lo;
+  const float* bias;
+  const float* cond;          // per-utterance vector added before the activation (or null)
+  const float* res;           // fp32 residual added to the fp32 output (or null)
+  float* y;                   // fp32 output rows (or null)
+  __nv_bfloat16* p_hi;        // split-bf16 planes of lrelu(out, pl_slope) for the next conv (or null)
+  __nv_bfloat16* p_lo;
+  int cond_ld, ldr, roff, ldy, yoff, ldp, poff;
+  int Cin, Cout, k, dil, pad;
+  int out_mul, out_add;       // output row = t*out_mul + out_add (polyphase ConvTranspose1d)
+  int in_extra, out_seq_extra;
+  int epi;
+  float alpha, pl_slope;
+};
+
+struct TcBatch {
+  TcProblem p[TC_MAXP];
+  int n;
+  int rmul;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile whose rows are 128 bytes apart (8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units, bits [0,14)
+  d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups, bits [32,46)
+  d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+template <int BN>
+constexpr int tc_smem_bytes() {
+  return TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  constexpr int A_BYTES = TC_BM * TC_BK * 2;           // 16 KB per plane
+  constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  const int pi = blockIdx.z % tb.n;
+  const int b = blockIdx.z / tb.n;
+  const TcProblem& P = tb.p[pi];
+  const int co0 = blockIdx.y * BN;
+  if (co0 >= P.Cout) return;
+  const int L = lens[b] * tb.rmul + P.in_extra;
+  const int t0 = blockIdx.x * TC_BM;
+  if (t0 >= L) return;
+  const long in_base = (long)offs[b] * tb.rmul + (long)b * P.in_extra;
+  const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
+
+  extern __shared__ uint8_t tc_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TC_STAGES;
+  uint64_t* tmem_full = empty_bar + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsteps = (P.Cin / TC_BK) * P.k;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_lo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_lo)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int s = 0; s < nsteps; ++s) {
+        const int st = s % TC_STAGES;
+        const int use = s / TC_STAGES;
+        if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);
+        const int c = s / P.k, j = s - c * P.k;
+        uint8_t* base = smem + st * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[st], STAGE_BYTES);
+        const int row = (int)in_base + t0 + j * P.dil - P.pad;
+        tma_load_2d(base, &P.a_hi, c * TC_BK, row, &full_bar[st]);
+        tma_load_2d(base + A_BYTES, &P.a_lo, c * TC_BK, row, &full_bar[st]);
+        tma_load_2d(base + 2 * A_BYTES, &P.w_hi, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
+        tma_load_2d(base + 2 * A_BYTES + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(BN);
+      for (int s = 0; s < nsteps; ++s) {
+        const int st = s % TC_STAGES;
+        mbar_wait(&full_bar[st], (s / TC_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t abase = smem_u32(smem + st * STAGE_BYTES);
+        const uint64_t ahi = umma_desc_sw128(abase), alo = umma_desc_sw128(abase + A_BYTES);
+        const uint64_t bhi = umma_desc_sw128(abase + 2 * A_BYTES), blo = umma_desc_sw128(abase + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 16; ++kk) {
+          const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
+          umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (s | kk) ? 1u : 0u);
+          umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+          umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
+        }
+        umma_commit(&empty_bar[st]);          // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);                 // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue: 4 warps, one TMEM lane quadrant each
+    const int quad = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int t = t0 + quad * 32 + lane;
+    const bool rowok = t < L;
+    const long orow = out_base + (long)t * P.out_mul + P.out_add;
+    const bool gate = (P.epi & TCE_GATE) != 0;
+#pragma unroll 1
+    for (int n0 = 0; n0 < BN; n0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0, v);
+      const int co = co0 + n0;
+      if (!rowok || co >= P.Cout) continue;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (co + i < P.Cout) {
+          float u = v[i] + P.bias[co + i];
+          if (P.cond) u += P.cond[(long)b * P.cond_ld + co + i];
+          v[i] = u;
+        }
+      }
+      int nout = 16, oc = co;
+      if (gate) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
+        nout = 8;
+        oc = co >> 1;
+      }
+      const int climit = gate ? (P.Cout >> 1) : P.Cout;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (i < nout) {
+          float u = v[i];
+          if (P.epi & TCE_RELU) u = fmaxf(u, 0.f);
+          u *= P.alpha;
+          if (P.res && oc + i < climit) u += P.res[orow * (long)P.ldr + P.roff + oc + i];
+          v[i] = u;
+        }
+      }
+      if (P.y) {
+        float* yr = P.y + orow * (long)P.ldy + P.yoff + oc;
+        if (oc + nout <= climit && (((P.ldy | P.yoff) & 3) == 0)) {
+          for (int i = 0; i < nout; i += 4) *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+          for (int i = 0; i < nout; ++i)
+            if (oc + i < climit) yr[i] = v[i];
+        }
+      }
+      if (P.p_hi) {
+        __nv_bfloat16* ph = P.p_hi + orow * (long)P.ldp + P.poff + oc;
+        __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + oc;
+        __align__(16) __nv_bfloat16 hb[16], lb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float u = i < nout ? v[i] : 0.f;
+          u = u > 0.f ? u : u * P.pl_slope;
+          split_bf16(u, hb[i], lb[i]);
+        }
+        if (oc + nout <= climit && (((P.ldp | P.poff) & 7) == 0)) {
+          for (int i = 0; i < nout; i += 8) {
+            *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb + i);
+            *reinterpret_cast<uint4*>(pl + i) = *reinterpret_cast<const uint4*>(lb + i);
+          }
+        } else {
+          for (int i = 0; i < nout; ++i)
+            if (oc + i < climit) { ph[i] = hb[i]; pl[i] = lb[i]; }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 rows -> split-bf16 planes (optionally through leaky-relu and the ReflectionPad1d((1,0)) row shift of
+// models.py:1039) for tensors that were not produced by a tensor-core epilogue.
+// ------------------------------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    int ldp, int C, float slope, int reflect, int rmul, const int* __restrict__ lens,
+                                    const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int Lphys = lens[b] * rmul;
+  const int L = Lphys + (reflect ? 1 : 0);
+  const int p = blockIdx.x;
+  if (p >= L) return;
+  const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
+  const long irow = (long)offs[b] * rmul + pr;
+  const long orow = (long)offs[b] * rmul + (reflect ? b : 0) + p;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(x + irow * ldx + c);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __align__(8) __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float u = f[i] > 0.f ? f[i] : f[i] * slope;
+      split_bf16(u, hb[i], lb[i]);
+    }
+    *reinterpret_cast<uint2*>(hi + orow * ldp + c) = *reinterpret_cast<const uint2*>(hb);
+    *reinterpret_cast<uint2*>(lo + orow * ldp + c) = *reinterpret_cast<const uint2*>(lb);
+  }
+}
+
+
+// MRF mean (models.py:1030-1036) that also emits the split-bf16 planes of leaky_relu(mean) for the next tensor-core
+// conv; with `reflect` the planes are written one row down and row 0 repeats row 1 (ReflectionPad1d((1,0))).
+__global__ void mrf_mean_planes_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c3, int n,
+                                       float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C,
+                                       float slope, int reflect, int rmul, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const int b = blockIdx.y;
+  const int Lphys = lens[b] * rmul;
+  const int L = Lphys + (reflect ? 1 : 0);
+  const int p = blockIdx.x;
+  if (p >= L) return;
+  const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
+  const long irow = (long)offs[b] * rmul + pr;
+  const long orow = (long)offs[b] * rmul + (reflect ? b : 0) + p;
+  const float d = (float)n;
+  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+    float4 s = *reinterpret_cast<const float4*>(a + irow * C + c);
+    if (n > 1) { const float4 u = *reinterpret_cast<const float4*>(b2 + irow * C + c); s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
+    if (n > 2) { const float4 u = *reinterpret_cast<const float4*>(c3 + irow * C + c); s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
+    s.x /= d; s.y /= d; s.z /= d; s.w /= d;
+    if (out && (!reflect || p >= 1)) *reinterpret_cast<float4*>(out + irow * C + c) = s;
+    const float f[4] = {s.x, s.y, s.z, s.w};
+    __align__(8) __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float u = f[i] > 0.f ? f[i] : f[i] * slope;
+      split_bf16(u, hb[i], lb[i]);
+    }
+    *reinterpret_cast<uint2*>(hi + orow * C + c) = *reinterpret_cast<const uint2*>(hb);
+    *reinterpret_cast<uint2*>(lo + orow * C + c) = *reinterpret_cast<const uint2*>(lb);
+  }
+}
+
+}  // namespace vtts

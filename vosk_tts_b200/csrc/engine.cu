@@ -18,6 +18,7 @@
 
 #include "../../include/vtts.h"
 #include "kernels.cuh"
+#include "conv_tc.cuh"
 
 using namespace vtts;
 
@@ -31,6 +32,26 @@ struct ConvW {
   const float* w = nullptr;
   const float* b = nullptr;
   int Cin = 0, Cout = 0, k = 0, ldw = 0;
+};
+struct TcW {     // split-bf16 copy of a conv weight: [k][Cout][Cin]
+  const __nv_bfloat16* hi = nullptr;
+  const __nv_bfloat16* lo = nullptr;
+};
+struct Planes {  // split-bf16 activation planes [rows][C]
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int C = 0;
+  long rows = 0;
+};
+struct TcSpec {  // one problem of a grouped tensor-core conv launch
+  Planes in;
+  TcW w;
+  const float* bias = nullptr;
+  int Cin = 0, Cout = 0, k = 1, dil = 1, pad = 0;
+  float* y = nullptr; int ldy = 0;
+  const float* res = nullptr; int ldr = 0;
+  Planes out; float pl_slope = 1.f;
+  int out_mul = 1, out_add = 0, in_extra = 0, out_seq_extra = 0;
 };
 struct LnW {
   const float* g = nullptr;
@@ -59,10 +80,12 @@ struct FlowW {
 };
 struct UpW {
   std::vector<ConvW> phase;
+  std::vector<TcW> tphase;
   std::vector<int> pad;
 };
 struct RbW {
   std::vector<ConvW> c1, c2;
+  std::vector<TcW> t1, t2;
 };
 
 template <typename T>
@@ -118,6 +141,17 @@ struct vtts_engine {
   std::vector<UpW> ups;
   std::vector<RbW> rbs;
   int hop = 0, up_total = 1;
+  bool tc = false;                      // precision mode 1: tcgen05 path for the decoder convs
+  TcW tc_pre, tc_post;
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn encode_tiled = nullptr;
+  Buf<__nv_bfloat16> pl_pool[64];       // plane buffers (hi/lo pairs), indexed by the decoder code
+  double tc_prof_flops = 0.0;
+  uint64_t tc_prof_launches = 0;
+  std::vector<cudaEvent_t> tc_prof_ev;
+  size_t tc_prof_used = 0;
 
   // ---- per-call state
   int B = 0, Ttok = 0, maxTok = 0, Tfrm = 0, maxFrm = 0;
@@ -132,9 +166,22 @@ struct vtts_engine {
   Buf<float> d_z, d_h, d_h1, d_wx, d_acts, d_skip, d_fqkv, d_fao, d_fy, d_ffh2, d_eps_z, d_d0, d_post, d_wav;
   std::vector<Buf<float>> d_stage;               // X_i
   std::vector<std::vector<Buf<float>>> d_xj, d_tmp;
+  // per-launch profiling of the conv kernel family (bench.py roofline): event pairs around each launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_ev;
+  size_t prof_used = 0;
+  double prof_flops = 0.0;
+  uint64_t prof_launches = 0;
   Buf<float> d_zp_dbg;                           // copy of z_p kept when debug_flags & 1
   int debug_flags = 0;
-  Buf<char> h_pin;                               // pinned staging (host)
+  Buf<char> h_pin, h_pin_in, h_pin_len, h_pin_z;  // pinned staging (host): outputs, phase-1 inputs, lengths, noise_z
+  Buf<float> d_prm;                              // per-call scalars (see kernels.cuh prm_seed)
+  // CUDA graphs: a call shape seen before is captured once and replayed (launch-bound at batch 1)
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
+  std::unordered_map<uint64_t, GraphEntry> graphs;
+  uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
+  bool capturing = false, use_graphs = true, last_graphed = false;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -143,26 +190,80 @@ struct vtts_engine {
   template <typename T>
   T* ensure(Buf<T>& b, size_t n) {
     if (n > b.cap) {
+      REQUIRE(!capturing, VTTS_ERR_STATE, "workspace growth during graph capture");
       if (b.p) CK(cudaFree(b.p));
       size_t cap = n + n / 4 + 256;
       CK(cudaMalloc(&b.p, cap * sizeof(T)));
       b.cap = cap;
+      ++ws_gen;                                // captured graphs hold the old pointers
     }
     return b.p;
   }
-  char* ensure_pinned(size_t n) {
-    if (n > h_pin.cap) {
-      if (h_pin.p) {
+  char* ensure_pinned(Buf<char>& hb, size_t n) {
+    if (n > hb.cap) {
+      REQUIRE(!capturing, VTTS_ERR_STATE, "staging growth during graph capture");
+      if (hb.p) {
         CK(cudaStreamSynchronize(stream));   // copies staged through the old buffer may still be in flight
-        CK(cudaFreeHost(h_pin.p));
-        h_pin.p = nullptr;
+        CK(cudaFreeHost(hb.p));
+        hb.p = nullptr;
       }
       size_t cap = n + n / 4 + 4096;
-      CK(cudaMallocHost(&h_pin.p, cap));
-      h_pin.cap = cap;
+      CK(cudaMallocHost(&hb.p, cap));
+      hb.cap = cap;
+      ++ws_gen;
     }
-    return h_pin.p;
+    return hb.p;
   }
+  char* ensure_pinned(size_t n) { return ensure_pinned(h_pin, n); }
+
+  // Runs `enqueue` (which only enqueues work on `stream`) eagerly the first time a shape key is seen, captures it
+  // into a CUDA graph the second time, and replays the graph afterwards.
+  template <typename Fn>
+  void run_graphed(uint64_t key, Fn&& enqueue) {
+    last_graphed = false;
+    if (!use_graphs || profiling || debug_flags) { enqueue(); return; }
+    GraphEntry& g = graphs[key];
+    if (g.exec && g.gen != ws_gen) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
+    g.used = ++graph_clock;
+    if (g.exec) {
+      CK(cudaGraphLaunch(g.exec, stream));
+      ++graph_replays;
+      launches += g.nlaunch;
+      last_graphed = true;
+      return;
+    }
+    if (g.seen++ == 0) { enqueue(); return; }   // first sighting: eager (also performs any workspace growth)
+    const uint64_t gen0 = ws_gen, l0 = launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    try {
+      enqueue();
+    } catch (...) {
+      capturing = false;
+      cudaStreamEndCapture(stream, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      throw;
+    }
+    capturing = false;
+    CK(cudaStreamEndCapture(stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) throw Err{VTTS_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)};
+    g.exec = exec;
+    g.gen = gen0;
+    g.nlaunch = launches - l0;
+    CK(cudaGraphLaunch(g.exec, stream));
+    ++graph_replays;
+    last_graphed = true;
+    if (graphs.size() > 64) {                  // bounded cache: drop the least recently used entry
+      uint64_t oldest = ~0ull, okey = 0;
+      for (auto& kv : graphs) if (kv.second.used < oldest) { oldest = kv.second.used; okey = kv.first; }
+      if (okey != key) { if (graphs[okey].exec) cudaGraphExecDestroy(graphs[okey].exec); graphs.erase(okey); }
+    }
+  }
+  static uint64_t mix(uint64_t h, uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return h; }
 
   Tensor tensor(const std::string& name) {
     auto it = tensors.find(name);
@@ -210,12 +311,39 @@ struct vtts_engine {
     return d;
   }
 
+  TcW tcw(const std::string& name, int Cin, int Cout, int k) {
+    TcW t;
+    const size_t n = (size_t)k * Cout * Cin / 2;
+    t.hi = reinterpret_cast<const __nv_bfloat16*>(vec(name + ".th", n));
+    t.lo = reinterpret_cast<const __nv_bfloat16*>(vec(name + ".tl", n));
+    REQUIRE(Cin % TC_BK == 0, VTTS_ERR_INVALID, "tensor-core conv needs input channels in multiples of 64");
+    return t;
+  }
+  Planes planes(int slot, long rows, int C, bool zero) {
+    Planes p;
+    p.C = C; p.rows = rows;
+    const size_t n = (size_t)rows * C + 64;
+    p.hi = ensure(pl_pool[2 * slot], n);
+    p.lo = ensure(pl_pool[2 * slot + 1], n);
+    if (zero) {     // gap rows between packed utterances must read as zero through TMA
+      CK(cudaMemsetAsync(p.hi, 0, n * sizeof(__nv_bfloat16), stream));
+      CK(cudaMemsetAsync(p.lo, 0, n * sizeof(__nv_bfloat16), stream));
+    }
+    return p;
+  }
+  CUtensorMap make_map(const void* base, int C, long rows, int box_rows);
+  void launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
+  void decoder_tc(float* z, const int* fl, const int* fo);
   void bind_weights();
   void launch_conv(const std::vector<ConvP>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   void encoder_layer(const EncLayerW& L, float*& x, float*& xb, float* qkv, float* ao, float* y, float* ffh, int Hc, int Fc,
                      int ks, const int* lens, const int* offs, int maxLen, const float* vec_after, int vec_ld,
                      const float* cadd_after);
   void dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, const int* lens, const int* offs, int maxLen);
+  struct P1Pin { int *len, *off, *sid, *ids; float *prm, *eps; };
+  P1Pin p1_layout(int t_max, bool eps);
+  void stage1(const int* ids_packed_host, const int* sid_host, int t_max, const float* noise_dp_host);
+  void finish1();
   void phase1(const int* ids_packed_host, const int64_t* d_ids64, int t_max, const int64_t* d_sid64, const int* sid_host,
               const float* noise_dp, bool noise_on_device);
   void phase2(const float* noise_z, int z_ld, bool noise_on_device);
@@ -288,6 +416,11 @@ void vtts_engine::bind_weights() {
     flow.push_back(F);
   }
   dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7);
+  tc = c.precision == 1;
+  if (tc) {
+    REQUIRE(c.decoder_type == 0 && c.resblock_type == 1, VTTS_ERR_INVALID, "tensor-core mode supports the MB-iSTFT / ResBlock1 decoder");
+    tc_pre = tcw("dec.pre", I, c.upsample_initial_channel, 7);
+  }
   ups.clear();
   rbs.clear();
   int ch = c.upsample_initial_channel;
@@ -300,6 +433,7 @@ void vtts_engine::bind_weights() {
       int d_min = -((r + p) / u);
       int d_max = (K - 1 - r - p) / u;
       U.phase.push_back(conv("dec.up" + std::to_string(i) + ".p" + std::to_string(r), ch, ch / 2, d_max - d_min + 1));
+      if (tc) U.tphase.push_back(tcw("dec.up" + std::to_string(i) + ".p" + std::to_string(r), ch, ch / 2, d_max - d_min + 1));
       U.pad.push_back(d_max);
     }
     ups.push_back(U);
@@ -312,6 +446,10 @@ void vtts_engine::bind_weights() {
         if (c.resblock_type == 1) {
           R.c1.push_back(conv(p2 + ".c1." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
           R.c2.push_back(conv(p2 + ".c2." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
+          if (tc) {
+            R.t1.push_back(tcw(p2 + ".c1." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
+            R.t2.push_back(tcw(p2 + ".c2." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
+          }
         } else {
           R.c1.push_back(conv(p2 + ".c." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
         }
@@ -324,6 +462,7 @@ void vtts_engine::bind_weights() {
   if (c.decoder_type == 0) {
     const int cps = c.istft_n_fft + 2;
     dec_post = conv("dec.post", ch, c.subbands * cps, 7);
+    if (tc) tc_post = tcw("dec.post", ch, c.subbands * cps, 7);
     istft_basis = vec("dec.istft", (size_t)cps * c.istft_n_fft);
     pqmf = vec("dec.pqmf", (size_t)c.subbands * 63);
     hop = up_total * c.istft_hop * c.subbands;
@@ -331,6 +470,177 @@ void vtts_engine::bind_weights() {
     dec_post = conv("dec.post", ch, 1, 7);
     hop = up_total;
   }
+}
+
+CUtensorMap vtts_engine::make_map(const void* base, int C, long rows, int box_rows) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Err{VTTS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+  return m;
+}
+
+// Grouped tensor-core conv launch (conv_tc.cuh).  One CTA = 128 rows x 64 output channels of one problem.
+void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB) {
+  constexpr int BN = 64;
+  REQUIRE(!ps.empty() && (int)ps.size() <= TC_MAXP, VTTS_ERR_INVALID, "bad grouped tensor-core conv");
+  static TcBatch tbs;   // 2.6 KB: keep it off the stack frame of every caller
+  TcBatch& tb = tbs;
+  memset(&tb, 0, sizeof(tb));
+  int maxCout = 0, maxL = 0;
+  for (size_t i = 0; i < ps.size(); ++i) {
+    const TcSpec& q = ps[i];
+    TcProblem& P = tb.p[i];
+    P.a_hi = make_map(q.in.hi, q.in.C, q.in.rows, TC_BM);
+    P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, TC_BM);
+    P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
+    P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN);
+    P.bias = q.bias;
+    P.res = q.res; P.ldr = q.ldr;
+    P.y = q.y; P.ldy = q.ldy;
+    P.p_hi = q.out.hi; P.p_lo = q.out.lo; P.ldp = q.out.C;
+    P.Cin = q.Cin; P.Cout = q.Cout; P.k = q.k; P.dil = q.dil; P.pad = q.pad;
+    P.out_mul = q.out_mul; P.out_add = q.out_add; P.in_extra = q.in_extra; P.out_seq_extra = q.out_seq_extra;
+    P.alpha = 1.f; P.pl_slope = q.pl_slope;
+    REQUIRE(q.in.C == q.Cin, VTTS_ERR_INVALID, "plane width must equal the conv input channels");
+    maxCout = std::max(maxCout, q.Cout);
+    maxL = std::max(maxL, maxLen * rmul + q.in_extra);
+  }
+  tb.n = (int)ps.size();
+  tb.rmul = rmul;
+  dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n);
+  if (grid.x == 0) return;
+  if (profiling) {
+    if (tc_prof_used + 2 > tc_prof_ev.size()) {
+      tc_prof_ev.resize(tc_prof_used + 2);
+      CK(cudaEventCreate(&tc_prof_ev[tc_prof_used]));
+      CK(cudaEventCreate(&tc_prof_ev[tc_prof_used + 1]));
+    }
+    for (const TcSpec& q : ps)
+      for (int b = 0; b < nB; ++b) tc_prof_flops += 2.0 * ((double)h_frm_len[b] * rmul + q.in_extra) * q.Cout * q.Cin * q.k;
+    ++tc_prof_launches;
+    CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
+  }
+  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes<BN>(), stream>>>(tb, lens, offs);
+  CK(cudaGetLastError());
+  if (profiling) {
+    CK(cudaEventRecord(tc_prof_ev[tc_prof_used + 1], stream));
+    tc_prof_used += 2;
+  }
+  ++launches;
+}
+
+// Decoder on the tensor cores (models.py:1016-1040): every conv consumes the split-bf16 planes written by its
+// producer's epilogue; fp32 copies exist only where a residual or the MRF mean needs them.
+void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
+  const vtts_config& c = cfg;
+  const int I = c.inter_channels;
+  const long F = Tfrm;
+  const bool zero = B > 1;
+  const int nk = c.n_resblock_kernels, nd = c.n_resblock_dilations;
+  int slot = 0;
+  Planes pz = planes(slot++, F, I, zero);
+  {
+    dim3 g(maxFrm, B);
+    split_planes_kernel<<<g, 64, 0, stream>>>(z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
+    CK(cudaGetLastError());
+    ++launches;
+  }
+  int ch = c.upsample_initial_channel;
+  Planes cur = planes(slot++, F, ch, zero);
+  {
+    TcSpec q;
+    q.in = pz; q.w = tc_pre; q.bias = dec_pre.b; q.Cin = I; q.Cout = ch; q.k = 7; q.dil = 1; q.pad = 3;
+    q.out = cur; q.pl_slope = 0.1f;
+    if (debug_flags & 1) { q.y = ensure(d_d0, (size_t)F * ch); q.ldy = ch; }
+    launch_tc({q}, 1, fl, fo, maxFrm, B);
+  }
+  int rm = 1;
+  if ((int)d_stage.size() < c.n_upsamples) {
+    d_stage.resize(c.n_upsamples);
+    d_xj.resize(c.n_upsamples);
+    d_tmp.resize(c.n_upsamples);
+    for (int i = 0; i < c.n_upsamples; ++i) { d_xj[i].resize(nk); d_tmp[i].resize(nk); }
+  }
+  float* lastX = nullptr;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    const int u = c.upsample_rates[i], ch2 = ch / 2;
+    const long rows = F * rm * u;
+    float* X = ensure(d_stage[i], (size_t)rows * ch2);
+    Planes px = planes(slot++, rows, ch2, zero);
+    for (int r0 = 0; r0 < u; r0 += TC_MAXP) {
+      std::vector<TcSpec> ps;
+      for (int r = r0; r < std::min(u, r0 + TC_MAXP); ++r) {
+        TcSpec q;
+        q.in = cur; q.w = ups[i].tphase[r]; q.bias = ups[i].phase[r].b; q.Cin = ch; q.Cout = ch2;
+        q.k = ups[i].phase[r].k; q.dil = 1; q.pad = ups[i].pad[r];
+        q.y = X; q.ldy = ch2; q.out = px; q.pl_slope = 0.1f; q.out_mul = u; q.out_add = r;
+        ps.push_back(q);
+      }
+      launch_tc(ps, rm, fl, fo, maxFrm, B);
+    }
+    rm *= u;
+    ch = ch2;
+    std::vector<float*> xj(nk);
+    std::vector<Planes> pj(nk), pt(nk);
+    for (int j = 0; j < nk; ++j) {
+      xj[j] = ensure(d_xj[i][j], (size_t)rows * ch);
+      pj[j] = planes(slot++, rows, ch, zero);
+      pt[j] = planes(slot++, rows, ch, zero);
+    }
+    for (int d = 0; d < nd; ++d) {
+      std::vector<TcSpec> p1, p2;
+      for (int j = 0; j < nk; ++j) {
+        const RbW& R = rbs[i * nk + j];
+        const int k = c.resblock_kernel_sizes[j], dl = c.resblock_dilations[j][d];
+        TcSpec a;
+        a.in = (d == 0) ? px : pj[j]; a.w = R.t1[d]; a.bias = R.c1[d].b; a.Cin = ch; a.Cout = ch; a.k = k; a.dil = dl;
+        a.pad = dl * (k - 1) / 2; a.out = pt[j]; a.pl_slope = 0.1f;
+        TcSpec b2;
+        b2.in = pt[j]; b2.w = R.t2[d]; b2.bias = R.c2[d].b; b2.Cin = ch; b2.Cout = ch; b2.k = k; b2.dil = 1; b2.pad = (k - 1) / 2;
+        b2.res = (d == 0) ? X : xj[j]; b2.ldr = ch; b2.y = xj[j]; b2.ldy = ch;
+        if (d + 1 < nd) { b2.out = pj[j]; b2.pl_slope = 0.1f; }
+        p1.push_back(a);
+        p2.push_back(b2);
+      }
+      launch_tc(p1, rm, fl, fo, maxFrm, B);
+      launch_tc(p2, rm, fl, fo, maxFrm, B);
+    }
+    const bool last = (i + 1 == c.n_upsamples);
+    Planes nxt = planes(slot++, rows + (last ? B : 0), ch, zero);
+    {
+      dim3 g(maxFrm * rm + (last ? 1 : 0), B);
+      mrf_mean_planes_kernel<<<g, 32, 0, stream>>>(xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
+                                                   (debug_flags & 1) ? X : nullptr, nxt.hi, nxt.lo, ch, last ? 0.01f : 0.1f,
+                                                   last ? 1 : 0, rm, fl, fo);
+      CK(cudaGetLastError());
+      ++launches;
+    }
+    cur = nxt;
+    lastX = X;
+  }
+  (void)lastX;
+  const int cps = c.istft_n_fft + 2, pc = c.subbands * cps;
+  float* post = ensure(d_post, ((size_t)F * rm + B) * pc);
+  {
+    TcSpec q;
+    q.in = cur; q.w = tc_post; q.bias = dec_post.b; q.Cin = ch; q.Cout = pc; q.k = 7; q.dil = 1; q.pad = 3;
+    q.y = post; q.ldy = pc; q.in_extra = 1; q.out_seq_extra = 1;
+    launch_tc({q}, rm, fl, fo, maxFrm, B);
+  }
+  float* wav = ensure(d_wav, (size_t)F * hop + 16);
+  const int M = maxFrm * rm * c.istft_hop;
+  dim3 g((M + TL_M - 1) / TL_M, B);
+  const size_t smem = ((size_t)(TL_M / 4 + 16) * pc + (size_t)c.subbands * (TL_M + 2 * (62 / 2 / c.subbands + 1))) * sizeof(float);
+  REQUIRE(c.istft_hop == 4 && c.istft_n_fft == 16, VTTS_ERR_INVALID, "iSTFT tail kernel is sized for n_fft=16, hop=4");
+  istft_pqmf_kernel<<<g, TL_THREADS, smem, stream>>>(post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
+  CK(cudaGetLastError());
+  ++launches;
 }
 
 void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB) {
@@ -347,13 +657,66 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   }
   cb.n = (int)ps.size();
   cb.rmul = rmul;
-  int xw = (CV_TT + maxHalo + 7) / 8 * 8 + 2;
+  int G = conv_max_g;
+  for (const ConvP& q : ps) {
+    while (G > 1 && q.Cin % (CV_CK * G) != 0) G >>= 1;
+  }
+  int xw = (CV_TT + maxHalo + 7) / 8 * 8 + 1;
   cb.xw = xw;
-  const size_t smem = (size_t)(CV_CK * xw + 2 * CV_CK * CV_TC) * sizeof(float);
-  dim3 grid((maxL + CV_TT - 1) / CV_TT, (maxCout + CV_TC - 1) / CV_TC, nB * cb.n);
+  const size_t pipe_floats = (size_t)2 * CV_CK * G * xw + (size_t)CV_NS * CV_CK * G * CV_TC;
+  const size_t red_floats = (size_t)G * 32 * CV_THREADS;
+  const size_t smem = std::max(pipe_floats, red_floats) * sizeof(float);
+  // cluster size: split the k-steps of every tile over S CTAs until the launch fills ~2 waves of SMs
+  const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+  long base = 0;
+  int minSteps = 1 << 30;
+  for (const ConvP& q : ps) {
+    for (int b = 0; b < nB; ++b)
+      base += (long)((hl[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
+    minSteps = std::min(minSteps, q.Cin / (CV_CK * G) * q.k);
+  }
+  int S = 1;
+  while (S < conv_max_s && base * S < conv_target && S * 2 <= minSteps) S *= 2;
+  cb.S = S;
+  dim3 grid(((maxL + CV_TT - 1) / CV_TT) * S, (maxCout + CV_TC - 1) / CV_TC, nB * cb.n);
   if (grid.x == 0) return;
-  conv_kernel<<<grid, CV_THREADS, smem, stream>>>(cb, lens, offs);
+  if (profiling) {
+    if (prof_used + 2 > prof_ev.size()) {
+      prof_ev.resize(prof_used + 2);
+      CK(cudaEventCreate(&prof_ev[prof_used]));
+      CK(cudaEventCreate(&prof_ev[prof_used + 1]));
+    }
+    for (const ConvP& q : ps)
+      for (int b = 0; b < nB; ++b)
+        prof_flops += 2.0 * ((double)hl[b] * rmul + q.in_extra) * q.Cout * q.Cin * q.k;
+    ++prof_launches;
+    CK(cudaEventRecord(prof_ev[prof_used], stream));
+  }
+  {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid;
+    lc.blockDim = dim3(CV_THREADS * G);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = S;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    lc.attrs = at;
+    lc.numAttrs = S > 1 ? 1 : 0;
+    switch (G) {
+      case 4: CK(cudaLaunchKernelEx(&lc, conv_kernel<4>, cb, lens, offs)); break;
+      case 2: CK(cudaLaunchKernelEx(&lc, conv_kernel<2>, cb, lens, offs)); break;
+      default: CK(cudaLaunchKernelEx(&lc, conv_kernel<1>, cb, lens, offs)); break;
+    }
+  }
   CK(cudaGetLastError());
+  if (profiling) {
+    CK(cudaEventRecord(prof_ev[prof_used + 1], stream));
+    prof_used += 2;
+  }
   ++launches;
 }
 
@@ -366,7 +729,7 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
   {
     const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
     dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, nB);
-    const size_t smem = (size_t)(2 * AT_KT * (dk + 1) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+    const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
     switch (dk / 32) {
       case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
       case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
@@ -403,7 +766,8 @@ void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, c
     P.ln2g = d[i].ln2.g; P.ln2b = d[i].ln2.b;
     P.C = C; P.k = k; P.dil = dil;
     dim3 grid((maxLen + DDS_TT - 1) / DDS_TT, B);
-    dds_layer_kernel<<<grid, C, 0, stream>>>(P, lens, offs);
+    const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * DDS_TT + 8 * DDS_TT) * sizeof(float);
+    dds_layer_kernel<<<grid, C, smem, stream>>>(P, lens, offs);
     CK(cudaGetLastError());
     ++launches;
     std::swap(a, b);
@@ -419,27 +783,21 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   const vtts_config& c = cfg;
   const int H = c.hidden_channels, I = c.inter_channels, D = c.dp_filter_channels, Fc = c.filter_channels;
   const size_t T = (size_t)Ttok;
-  CK(cudaEventRecord(ev[0], stream));
-  // ---- inputs
+  if (!capturing) CK(cudaEventRecord(ev[0], stream));
+  // ---- inputs (host data was staged into h_pin_in by stage1(); only device work is enqueued here)
   int* tl = ensure(d_tok_len, B);
   int* to = ensure(d_tok_off, B + 1);
   int* ids = ensure(d_ids, T);
   int* sid = ensure(d_sid, B);
+  float* prm = ensure(d_prm, 8);
   {
-    char* pin = ensure_pinned((size_t)(2 * B + 1 + B) * sizeof(int) + T * sizeof(int) + (size_t)B * 2 * t_max * sizeof(float) + 64);
-    int* p_len = reinterpret_cast<int*>(pin);
-    int* p_off = p_len + B;
-    int* p_sid = p_off + B + 1;
-    int* p_ids = p_sid + B;
-    memcpy(p_len, h_tok_len.data(), B * sizeof(int));
-    memcpy(p_off, h_tok_off.data(), (B + 1) * sizeof(int));
-    CK(cudaMemcpyAsync(tl, p_len, B * sizeof(int), cudaMemcpyHostToDevice, stream));
-    CK(cudaMemcpyAsync(to, p_off, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    P1Pin pp = p1_layout(t_max, noise_dp && !noise_on_device);
+    CK(cudaMemcpyAsync(tl, pp.len, B * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(to, pp.off, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(prm, pp.prm, 8 * sizeof(float), cudaMemcpyHostToDevice, stream));
     if (ids_packed_host) {
-      memcpy(p_ids, ids_packed_host, T * sizeof(int));
-      memcpy(p_sid, sid_host, B * sizeof(int));
-      CK(cudaMemcpyAsync(ids, p_ids, T * sizeof(int), cudaMemcpyHostToDevice, stream));
-      CK(cudaMemcpyAsync(sid, p_sid, B * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(ids, pp.ids, T * sizeof(int), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(sid, pp.sid, B * sizeof(int), cudaMemcpyHostToDevice, stream));
     } else {
       dim3 g((maxTok + 127) / 128, B);
       pack_ids_kernel<<<g, 128, 0, stream>>>(d_ids64, t_max, ids, tl, to);
@@ -449,14 +807,12 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
       launches += 2;
     }
     if (noise_dp && !noise_on_device) {
-      float* p_eps = reinterpret_cast<float*>(p_ids + T);
-      memcpy(p_eps, noise_dp, (size_t)B * 2 * t_max * sizeof(float));
       float* de = ensure(d_eps_dp, (size_t)B * 2 * t_max);
-      CK(cudaMemcpyAsync(de, p_eps, (size_t)B * 2 * t_max * sizeof(float), cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(de, pp.eps, (size_t)B * 2 * t_max * sizeof(float), cudaMemcpyHostToDevice, stream));
       noise_dp = de;
     }
   }
-  CK(cudaEventRecord(ev[1], stream));
+  if (!capturing) CK(cudaEventRecord(ev[1], stream));
 
   // ---- speaker conditioning (models.py:1680-1683)
   float* condv = nullptr;
@@ -489,7 +845,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     encoder_layer(enc[i], x, xb, qkv, ao, y, ffh, H, Fc, c.kernel_size, tl, to, maxTok, va, condR, nullptr);
   }
   launch_conv({mk(enc_proj, x, H, 0, stats, 2 * I, 0, 1, 0)}, 1, tl, to, maxTok, B);
-  CK(cudaEventRecord(ev[2], stream));
+  if (!capturing) CK(cudaEventRecord(ev[2], stream));
 
   // ---- stochastic duration predictor, reverse (models.py:56-63, 93-101)
   float* dA = ensure(d_dA, T * D);
@@ -510,7 +866,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   }
   {
     dim3 g((maxTok + 127) / 128, B);
-    dp_noise_kernel<<<g, 128, 0, stream>>>(noise_dp, t_max, seed, scales[2], za, zb, tl, to);
+    dp_noise_kernel<<<g, 128, 0, stream>>>(noise_dp, t_max, prm, za, zb, tl, to);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -543,22 +899,56 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   int* cum = ensure(d_cum, T);
   int* fl = ensure(d_frm_len, B);
   int* fo = ensure(d_frm_off, B + 1);
-  duration_kernel<<<B, 256, 0, stream>>>(zlast, dp_ea, 0, 2, scales[1], wceil, cum, fl, tl, to);
+  duration_kernel<<<B, 256, 0, stream>>>(zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to);
   CK(cudaGetLastError());
   frame_offsets_kernel<<<1, 32, 0, stream>>>(fl, fo, B);
   CK(cudaGetLastError());
   launches += 2;
-  CK(cudaEventRecord(ev[3], stream));
+  if (!capturing) CK(cudaEventRecord(ev[3], stream));
   {
-    char* pin = ensure_pinned((size_t)(2 * B + 2) * sizeof(int) + T * sizeof(int) + 64);
-    int* p_len = reinterpret_cast<int*>(pin);
-    int* p_off = p_len + B;
+    int* p_len = reinterpret_cast<int*>(ensure_pinned(h_pin_len, (size_t)(2 * B + 2) * sizeof(int)));
     CK(cudaMemcpyAsync(p_len, fl, B * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaMemcpyAsync(p_off, fo, (B + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CK(cudaStreamSynchronize(stream));
-    h_frm_len.assign(p_len, p_len + B);
-    h_frm_off.assign(p_off, p_off + B + 1);
+    CK(cudaMemcpyAsync(p_len + B, fo, (B + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
   }
+}
+
+// Host side of phase 1: stage the call's inputs in pinned memory (fixed layout, so a captured graph can re-read it).
+vtts_engine::P1Pin vtts_engine::p1_layout(int t_max, bool eps) {
+  const size_t T = (size_t)Ttok;
+  const size_t bytes = (size_t)(3 * B + 1) * sizeof(int) + T * sizeof(int) + 8 * sizeof(float) +
+                       (eps ? (size_t)B * 2 * t_max * sizeof(float) : 0) + 64;
+  char* pin = ensure_pinned(h_pin_in, bytes);
+  P1Pin pp;
+  pp.len = reinterpret_cast<int*>(pin);
+  pp.off = pp.len + B;
+  pp.sid = pp.off + B + 1;
+  pp.ids = pp.sid + B;
+  pp.prm = reinterpret_cast<float*>(pp.ids + T);
+  pp.eps = pp.prm + 8;
+  return pp;
+}
+
+void vtts_engine::stage1(const int* ids_packed_host, const int* sid_host, int t_max, const float* noise_dp_host) {
+  P1Pin pp = p1_layout(t_max, noise_dp_host != nullptr);
+  memcpy(pp.len, h_tok_len.data(), B * sizeof(int));
+  memcpy(pp.off, h_tok_off.data(), (B + 1) * sizeof(int));
+  if (ids_packed_host) {
+    memcpy(pp.ids, ids_packed_host, (size_t)Ttok * sizeof(int));
+    memcpy(pp.sid, sid_host, B * sizeof(int));
+  }
+  pp.prm[0] = scales[0]; pp.prm[1] = scales[1]; pp.prm[2] = scales[2]; pp.prm[3] = 0.f;
+  const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+  memcpy(&pp.prm[4], &lo, 4);
+  memcpy(&pp.prm[5], &hi, 4);
+  pp.prm[6] = pp.prm[7] = 0.f;
+  if (noise_dp_host) memcpy(pp.eps, noise_dp_host, (size_t)B * 2 * t_max * sizeof(float));
+}
+
+void vtts_engine::finish1() {
+  CK(cudaStreamSynchronize(stream));
+  const int* p_len = reinterpret_cast<const int*>(h_pin_len.p);
+  h_frm_len.assign(p_len, p_len + B);
+  h_frm_off.assign(p_len + B, p_len + 2 * B + 1);
   Tfrm = h_frm_off[B];
   maxFrm = 0;
   for (int b = 0; b < B; ++b) maxFrm = std::max(maxFrm, h_frm_len[b]);
@@ -576,21 +966,19 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
   const int* to = d_tok_off.p;
   const int* fl = d_frm_len.p;
   const int* fo = d_frm_off.p;
-  CK(cudaEventRecord(ev[4], stream));
+  if (!capturing) CK(cudaEventRecord(ev[4], stream));
   if (noise_z && !noise_on_device) {
+    // host noise was staged into h_pin_z by the caller (vtts_synthesize)
     const size_t n = (size_t)B * I * z_ld;
     float* de = ensure(d_eps_z, n);
-    // caller memory may be pageable: stage through the pinned buffer
-    char* pin = ensure_pinned(n * sizeof(float));
-    memcpy(pin, noise_z, n * sizeof(float));
-    CK(cudaMemcpyAsync(de, pin, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+    CK(cudaMemcpyAsync(de, h_pin_z.p, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     noise_z = de;
   }
   float* z = ensure(d_z, F * I);
   int* ftok = ensure(d_ftok, F);
   {
     dim3 g(maxFrm, B);
-    sample_prior_kernel<<<g, 64, 0, stream>>>(d_stats.p, I, d_cum.p, tl, to, fl, fo, noise_z, z_ld, seed, scales[0], z, ftok);
+    sample_prior_kernel<<<g, 64, 0, stream>>>(d_stats.p, I, d_cum.p, tl, to, fl, fo, noise_z, z_ld, d_prm.p, z, ftok);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -628,7 +1016,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
       {
         const int dk = H / c.n_heads, nrel = 2 * c.window_size + 1;
         dim3 grid((maxFrm + AT_QT - 1) / AT_QT, c.n_heads, B);
-        const size_t smem = (size_t)(2 * AT_KT * (dk + 1) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+        const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
         switch (dk / 32) {
           case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
           case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
@@ -682,9 +1070,14 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
       launch_conv({p}, 1, fl, fo, maxFrm, B);
     }
   }
-  CK(cudaEventRecord(ev[5], stream));
+  if (!capturing) CK(cudaEventRecord(ev[5], stream));
 
   // ---- decoder (models.py:1016-1054 / 872-891)
+  if (tc) {
+    decoder_tc(z, fl, fo);
+    if (!capturing) CK(cudaEventRecord(ev[6], stream));
+    return;
+  }
   int ch = c.upsample_initial_channel;
   float* cur = ensure(d_d0, F * ch);
   launch_conv({mk(dec_pre, z, I, 0, cur, ch, 0, 1, 3)}, 1, fl, fo, maxFrm, B);
@@ -776,7 +1169,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
     p.epi = EPI_TANH;
     launch_conv({p}, rm, fl, fo, maxFrm, B);
   }
-  CK(cudaEventRecord(ev[6], stream));
+  if (!capturing) CK(cudaEventRecord(ev[6], stream));
 }
 
 // ===================================================================================================
@@ -806,6 +1199,11 @@ int guarded(vtts_handle h, Fn fn) {
 void collect_timings(vtts_handle h) {
   // ev: 0 start, 1 after H2D, 2 after encoder, 3 after dp, 4 phase2 start, 5 after flow, 6 after decoder, 7 after D2H
   float t;
+  if (h->last_graphed) {      // stage events are not recorded inside captured graphs
+    for (float& v : h->stage_ms) v = 0.f;
+    cudaGetLastError();
+    return;
+  }
   cudaEventElapsedTime(&t, h->ev[1], h->ev[2]); h->stage_ms[0] = t;
   cudaEventElapsedTime(&t, h->ev[2], h->ev[3]); h->stage_ms[1] = t;
   cudaEventElapsedTime(&t, h->ev[4], h->ev[5]); h->stage_ms[2] = t;
@@ -824,7 +1222,7 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
     REQUIRE(lengths[b] >= 1 && lengths[b] <= t_max, VTTS_ERR_INVALID, "input_lengths must be in [1, t_max]");
     h->h_tok_len[b] = (int)lengths[b];
     h->h_tok_off[b] = off;
-    off += (int)lengths[b];
+    off += (int)lengths[b] + (b + 1 < B ? SEQ_GAP : 0);
     mx = std::max(mx, (int)lengths[b]);
   }
   h->h_tok_off[B] = off;
@@ -846,7 +1244,15 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
   h->device = device;
   *out = h;   // returned even on failure so that vtts_last_error() is readable; caller destroys it
   return guarded(h, [&] {
-    REQUIRE(cfg->precision == 0, VTTS_ERR_INVALID, "precision mode not built into this library");
+    REQUIRE(cfg->precision == 0 || cfg->precision == 1, VTTS_ERR_INVALID, "unknown precision mode");
+    if (cfg->precision == 1) {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult qres;
+      CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+      REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+      h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
+    }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
     h->blob_floats = blob_floats;
@@ -859,8 +1265,19 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       REQUIRE(off + n <= blob_floats, VTTS_ERR_WEIGHTS, "manifest entry exceeds the blob");
       h->tensors[name] = Tensor{h->d_blob + off, (size_t)n};
     }
+    if (const char* e = getenv("VTTS_CONV_MAXS")) h->conv_max_s = std::max(1, atoi(e));
+    if (const char* e = getenv("VTTS_CONV_TARGET")) h->conv_target = std::max(1, atoi(e));
+    if (const char* e = getenv("VTTS_CONV_MAXG")) h->conv_max_g = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     h->bind_weights();
-    CK(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CK(cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK(cudaStreamSynchronize(h->stream));
   });
 }
@@ -880,8 +1297,13 @@ void vtts_destroy(vtts_handle h) {
   for (auto& b : h->d_stage) fr(b.p);
   for (auto& v : h->d_xj) for (auto& b : v) fr(b.p);
   for (auto& v : h->d_tmp) for (auto& b : v) fr(b.p);
-  if (h->h_pin.p) cudaFreeHost(h->h_pin.p);
+  for (Buf<char>* hb : {&h->h_pin, &h->h_pin_in, &h->h_pin_len, &h->h_pin_z}) if (hb->p) cudaFreeHost(hb->p);
+  for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  fr(h->d_prm.p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->prof_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->tc_prof_ev) if (e) cudaEventDestroy(e);
+  for (auto& b : h->pl_pool) fr(b.p);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -900,7 +1322,13 @@ int vtts_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, co
       for (int t = 0; t < h->h_tok_len[b]; ++t) packed[h->h_tok_off[b] + t] = (int)ids[(size_t)b * t_max + t];
       sid32[b] = (int)sid[b];
     }
-    h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false);
+    h->stage1(packed.data(), sid32.data(), t_max, noise_dp);
+    uint64_t key = vtts_engine::mix(0x11, (uint64_t)B);
+    key = vtts_engine::mix(key, (uint64_t)t_max);
+    key = vtts_engine::mix(key, noise_dp ? 1 : 0);
+    for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
+    h->run_graphed(key, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
+    h->finish1();
     for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
     if (durations) {
       std::vector<int> wc(h->Ttok);
@@ -921,7 +1349,16 @@ int vtts_synthesize(vtts_handle h, const float* noise_z, int z_ld, float* wav, i
     REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
     REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
     REQUIRE(!frame_token || idx_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
-    h->phase2(noise_z, z_ld, false);
+    if (noise_z) {
+      const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
+      char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));   // caller memory may be pageable
+      memcpy(pin, noise_z, n * sizeof(float));
+    }
+    uint64_t key = vtts_engine::mix(0x22, (uint64_t)h->B);
+    key = vtts_engine::mix(key, (uint64_t)z_ld);
+    key = vtts_engine::mix(key, noise_z ? 1 : 0);
+    for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
+    h->run_graphed(key, [&] { h->phase2(noise_z, z_ld, false); });
     const size_t nw = (size_t)h->Tfrm * h->hop;
     char* pin = h->ensure_pinned(nw * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
     float* pw = reinterpret_cast<float*>(pin);
@@ -946,7 +1383,15 @@ int vtts_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengt
     setup_lengths(h, lengths_host, B, t_max);
     memcpy(h->scales, scales, 3 * sizeof(float));
     h->seed = seed;
-    h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true);
+    h->stage1(nullptr, nullptr, t_max, nullptr);
+    uint64_t key = vtts_engine::mix(0x33, (uint64_t)B);
+    key = vtts_engine::mix(key, (uint64_t)t_max);
+    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_ids);
+    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_sid);
+    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_dp);
+    for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
+    h->run_graphed(key, [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
+    h->finish1();
     for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
   });
 }
@@ -957,7 +1402,11 @@ int vtts_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* 
     REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize_dev called without vtts_durations_dev");
     REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
     REQUIRE(!d_noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-    h->phase2(d_noise_z, z_ld, true);
+    uint64_t key = vtts_engine::mix(0x44, (uint64_t)h->B);
+    key = vtts_engine::mix(key, (uint64_t)z_ld);
+    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_z);
+    for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
+    h->run_graphed(key, [&] { h->phase2(d_noise_z, z_ld, true); });
     for (int b = 0; b < h->B; ++b)
       CK(cudaMemcpyAsync(d_wav + (size_t)b * wav_ld, h->d_wav.p + (size_t)h->h_frm_off[b] * h->hop,
                          (size_t)h->h_frm_len[b] * h->hop * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -978,6 +1427,40 @@ int vtts_stage_timings(vtts_handle h, float* ms, int n) {
 
 uint64_t vtts_kernel_launches(vtts_handle h) { return h ? h->launches : 0; }
 void* vtts_stream(vtts_handle h) { return h ? (void*)h->stream : nullptr; }
+
+int vtts_set_graphs(vtts_handle h, int enable) {
+  return guarded(h, [&] { h->use_graphs = enable != 0; });
+}
+
+uint64_t vtts_graph_replays(vtts_handle h) { return h ? h->graph_replays : 0; }
+
+int vtts_profile(vtts_handle h, int enable) {
+  return guarded(h, [&] {
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    h->prof_flops = 0.0;
+    h->prof_launches = 0;
+    h->tc_prof_used = 0;
+    h->tc_prof_flops = 0.0;
+    h->tc_prof_launches = 0;
+  });
+}
+
+int vtts_profile_read(vtts_handle h, double* conv_ms, uint64_t* conv_launches, double* conv_flops) {
+  if (!conv_ms || !conv_launches || !conv_flops) return VTTS_ERR_INVALID;
+  return guarded(h, [&] {
+    CK(cudaStreamSynchronize(h->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->prof_used; i += 2) {
+      float t = 0.f;
+      CK(cudaEventElapsedTime(&t, h->prof_ev[i], h->prof_ev[i + 1]));
+      ms += t;
+    }
+    *conv_ms = ms;
+    *conv_launches = h->prof_launches;
+    *conv_flops = h->prof_flops;
+  });
+}
 
 int vtts_debug_flags(vtts_handle h, int flags) {
   if (!h) return VTTS_ERR_INVALID;
@@ -1015,6 +1498,22 @@ int vtts_debug_read(vtts_handle h, const char* name, float* out, size_t max_floa
     CK(cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *n_out = n;
+  });
+}
+
+int vtts_profile_read_tc(vtts_handle h, double* ms, uint64_t* launches, double* flops) {
+  if (!ms || !launches || !flops) return VTTS_ERR_INVALID;
+  return guarded(h, [&] {
+    CK(cudaStreamSynchronize(h->stream));
+    double t = 0.0;
+    for (size_t i = 0; i + 1 < h->tc_prof_used; i += 2) {
+      float e = 0.f;
+      CK(cudaEventElapsedTime(&e, h->tc_prof_ev[i], h->tc_prof_ev[i + 1]));
+      t += e;
+    }
+    *ms = t;
+    *launches = h->tc_prof_launches;
+    *flops = h->tc_prof_flops;
   });
 }
 

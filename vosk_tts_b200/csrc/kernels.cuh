@@ -53,7 +53,8 @@ struct ConvBatch {
   ConvP p[CV_MAXP];
   int n;
   int rmul;  // rows per length unit of the input (1, 4, 16 ...)
-  int xw;    // smem row pitch of the input tile (floats), == 2 (mod 8)
+  int xw;    // smem row pitch of the input tile (floats), == 1 (mod 8)
+  int S;     // thread-block-cluster size along grid.x: the k-steps of a tile are split over S CTAs
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
@@ -64,32 +65,66 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(CV_THREADS)
+// thread-block-cluster barrier (all threads of all CTAs) with release/acquire semantics
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// load a float from the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, int rank) {
+  unsigned la = (unsigned)__cvta_generic_to_shared(local_smem_ptr), ra;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(ra) : "r"(la), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(ra) : "memory");
+  return v;
+}
+
+// Work decomposition (one CTA = one 64(time) x 64(channel) output tile of one problem of one utterance):
+//  * G thread groups of 128 split the 16*G input channels of every k-step (intra-CTA split-K);
+//  * S CTAs of a thread-block cluster split the k-steps (s = rank, rank+S, ...) and reduce their partial
+//    tiles through distributed shared memory in a fixed order (deterministic), each CTA finishing 1/S of
+//    the tile.  At batch 1 a conv has only a handful of output tiles; the cluster dimension is what lets
+//    it spread over the 148 SMs.
+//  * inside a group each thread accumulates 4 rows (tx + 16m) x 8 channels (shared-memory operand delivery is
+//    128 B/clk/SM of *delivered* data, so wider register tiles than the 2x16 variant tried first are needed).
+// Weight tiles run through an NS-deep cp.async ring (one __syncthreads per step); the input tile of the
+// next needed channel chunk is prefetched into registers (prologue applied) and double-buffered.
+constexpr int CV_NS = 3;
+
+template <int G>
+__global__ void __launch_bounds__(CV_THREADS * G)
 conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  constexpr int CKS = CV_CK * G;        // channels per step over all groups
+  constexpr int NT = CV_THREADS * G;
+  const int S = cb.S;                   // cluster size along x (1, 2, 4, 8)
+  const int rank = S > 1 ? (int)(blockIdx.x % S) : 0;
   const int pi = blockIdx.z % cb.n;
   const int b = blockIdx.z / cb.n;
   const ConvP& P = cb.p[pi];
   const int co0 = blockIdx.y * CV_TC;
-  if (co0 >= P.Cout) return;
+  if (co0 >= P.Cout) return;            // uniform over the cluster
   const int Lphys = lens[b] * cb.rmul;
   const int L = Lphys + P.in_extra;
-  const int t0 = blockIdx.x * CV_TT;
-  if (t0 >= L) return;
+  const int t0 = (int)(blockIdx.x / S) * CV_TT;
+  if (t0 >= L) return;                  // uniform over the cluster
   const long in_base = (long)offs[b] * cb.rmul;
   const long out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
 
   extern __shared__ __align__(16) float smem[];
   const int xw = cb.xw;
-  float* Xs = smem;                 // [CK][xw]
-  float* Ws = smem + CV_CK * xw;    // [2][CK][TC]
+  float* Xs = smem;                      // [2][CKS][xw]
+  float* Ws = smem + 2 * CKS * xw;       // [NS][CKS][TC]
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15;
-  const int ty = tid >> 4;
+  const int grp = tid / CV_THREADS;
+  const int ltid = tid - grp * CV_THREADS;
+  const int tx = ltid & 15;              // time rows tx + 16*m
+  const int ty = ltid >> 4;              // 8-channel strip
   const int k = P.k, dil = P.dil;
   const int n_pos = CV_TT + (k - 1) * dil;
-  const int nchunks = P.Cin / CV_CK;
+  const int nchunks = P.Cin / CKS;
   const int nsteps = nchunks * k;
+  const int nmine = nsteps > rank ? (nsteps - rank + S - 1) / S : 0;   // my steps: rank, rank+S, ...
 
   float acc[4][8];
 #pragma unroll
@@ -102,15 +137,15 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   auto load_x = [&](int c) {
 #pragma unroll
     for (int e = 0; e < CV_XR; ++e) {
-      const int it = tid + e * CV_THREADS;
+      const int it = tid + e * NT;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (it < n_pos * 4) {
-        const int pos = it >> 2;
-        const int q = (it & 3) * 4;
+      if (it < n_pos * 4 * G) {
+        const int pos = it / (4 * G);
+        const int q = (it - pos * 4 * G) * 4;
         const int p = t0 + pos - P.pad;
         if (p >= 0 && p < L) {
           const int pr = P.reflect ? (p == 0 ? 1 : p - 1) : p;
-          v = __ldg(reinterpret_cast<const float4*>(P.x + (in_base + pr) * (long)P.ldx + P.xoff + c * CV_CK + q));
+          v = __ldg(reinterpret_cast<const float4*>(P.x + (in_base + pr) * (long)P.ldx + P.xoff + c * CKS + q));
           if (P.pro == PRO_LRELU) {
             v.x = v.x > 0.f ? v.x : v.x * P.slope;
             v.y = v.y > 0.f ? v.y : v.y * P.slope;
@@ -122,125 +157,191 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
       xr[e] = v;
     }
   };
-  auto store_x = [&]() {
+  auto store_x = [&](int xb) {
+    float* dst = Xs + xb * CKS * xw;
 #pragma unroll
     for (int e = 0; e < CV_XR; ++e) {
-      const int it = tid + e * CV_THREADS;
-      if (it < n_pos * 4) {
-        const int pos = it >> 2;
-        const int q = (it & 3) * 4;
-        Xs[(q + 0) * xw + pos] = xr[e].x;
-        Xs[(q + 1) * xw + pos] = xr[e].y;
-        Xs[(q + 2) * xw + pos] = xr[e].z;
-        Xs[(q + 3) * xw + pos] = xr[e].w;
+      const int it = tid + e * NT;
+      if (it < n_pos * 4 * G) {
+        const int pos = it / (4 * G);
+        const int q = (it - pos * 4 * G) * 4;
+        dst[(q + 0) * xw + pos] = xr[e].x;
+        dst[(q + 1) * xw + pos] = xr[e].y;
+        dst[(q + 2) * xw + pos] = xr[e].z;
+        dst[(q + 3) * xw + pos] = xr[e].w;
       }
     }
   };
-  auto issue_w = [&](int s, int buf) {
+  auto issue_w = [&](int i) {            // i-th of my steps
+    const int s = rank + i * S;
     const int c = s / k, j = s - c * k;
+    float* dst = Ws + (i % CV_NS) * CKS * CV_TC;
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int f = tid + e * CV_THREADS;
+      const int f = tid + e * NT;
       const int r = f >> 4;
       const int c4 = (f & 15) * 4;
       const bool ok = (co0 + c4) < P.ldw;
-      const float* src = P.w + ((long)(j * P.Cin + c * CV_CK + r) * P.ldw + (ok ? co0 + c4 : 0));
-      cp_async16(Ws + (buf * CV_CK + r) * CV_TC + c4, src, ok ? 16 : 0);
+      const float* src = P.w + ((long)(j * P.Cin + c * CKS + r) * P.ldw + (ok ? co0 + c4 : 0));
+      cp_async16(dst + r * CV_TC + c4, src, ok ? 16 : 0);
     }
   };
 
-  load_x(0);
-  store_x();
-  issue_w(0, 0);
-  cp_async_commit();
-  int buf = 0;
-  for (int c = 0; c < nchunks; ++c) {
-    if (c + 1 < nchunks) load_x(c + 1);
-    for (int j = 0; j < k; ++j) {
-      const int s = c * k + j;
-      if (s + 1 < nsteps) issue_w(s + 1, buf ^ 1);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncthreads();
-      const float* xs = Xs + tx + j * dil;
-      const float* ws = Ws + buf * CV_CK * CV_TC + ty * 8;
+  int xbuf = 0;        // Xs buffer holding chunk `ccur`
+  int ccur = -1;
+  if (nmine > 0) {
+    ccur = rank / k;
+    load_x(ccur);
+    store_x(0);
+  }
 #pragma unroll
-      for (int ci = 0; ci < CV_CK; ++ci) {
-        float a[4];
+  for (int i = 0; i < CV_NS - 1; ++i) {
+    if (i < nmine) issue_w(i);
+    cp_async_commit();
+  }
+  for (int i = 0; i < nmine; ++i) {
+    const int s = rank + i * S;
+    const int c = s / k, j = s - c * k;
+    // chunk needed by my next step (prefetch into registers while this step computes)
+    const int cnext = (i + 1 < nmine) ? (s + S) / k : c;
+    const bool fetch = cnext != c;
+    if (fetch) load_x(cnext);
+    cp_async_wait<CV_NS - 2>();
+    __syncthreads();                       // W[i] (and a freshly stored X chunk) visible; ring slot (i-1)%NS free
+    if (i + CV_NS - 1 < nmine) issue_w(i + CV_NS - 1);
+    cp_async_commit();
+    const float* xs = Xs + (xbuf * CKS + grp * CV_CK) * xw + tx + j * dil;
+    const float* ws = Ws + ((i % CV_NS) * CKS + grp * CV_CK) * CV_TC + ty * 8;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) a[m] = xs[ci * xw + 16 * m];
-        const float4 b0 = *reinterpret_cast<const float4*>(ws + ci * CV_TC);
-        const float4 b1 = *reinterpret_cast<const float4*>(ws + ci * CV_TC + 4);
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    for (int ci = 0; ci < CV_CK; ++ci) {
+      float a[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) a[m] = xs[ci * xw + 16 * m];
+      const float4 b0 = *reinterpret_cast<const float4*>(ws + ci * CV_TC);
+      const float4 b1 = *reinterpret_cast<const float4*>(ws + ci * CV_TC + 4);
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(a[m], bb[n], acc[m][n]);
+    }
+    if (fetch) {                            // other buffer was last read >= 1 barrier ago
+      store_x(xbuf ^ 1);
+      xbuf ^= 1;
+    }
+  }
+
+  // ---- reductions: groups (shared memory) then cluster ranks (distributed shared memory), fixed order
+  cp_async_wait<0>();
+  __syncthreads();
+  float* red = smem;                                       // [G-1][32][128]
+  float* part = smem + (G - 1) * 32 * CV_THREADS;          // [32][128] this CTA's partial tile
+  if (G > 1) {
+    if (grp > 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) red[((grp - 1) * 32 + m * 8 + n) * CV_THREADS + ltid] = acc[m][n];
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int g2 = 0; g2 < G - 1; ++g2)
 #pragma unroll
         for (int m = 0; m < 4; ++m)
 #pragma unroll
-          for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(a[m], bb[n], acc[m][n]);
-      }
-      __syncthreads();
-      buf ^= 1;
+          for (int n = 0; n < 8; ++n) acc[m][n] += red[(g2 * 32 + m * 8 + n) * CV_THREADS + ltid];
     }
-    if (c + 1 < nchunks) store_x();
   }
+  // ownership of the 4 x 2 (row, 4-column chunk) units of each thread among the S ranks
+  int m_lo = 0, m_hi = 4, q_lo = 0, q_hi = 2;
+  if (S > 1) {
+    if (grp == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int n = 0; n < 8; ++n) part[(m * 8 + n) * CV_THREADS + ltid] = acc[m][n];
+    }
+    cluster_sync_all();
+    if (S == 2) { m_lo = 2 * rank; m_hi = m_lo + 2; }
+    else if (S == 4) { m_lo = rank; m_hi = rank + 1; }
+    else { m_lo = rank >> 1; m_hi = m_lo + 1; q_lo = rank & 1; q_hi = q_lo + 1; }
+    if (grp == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (m >= m_lo && m < m_hi && q >= q_lo && q < q_hi) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int idx = (m * 8 + q * 4 + e) * CV_THREADS + ltid;
+              float v = 0.f;
+              for (int r2 = 0; r2 < S; ++r2) v += ld_dsmem(part + idx, r2);
+              acc[m][q * 4 + e] = v;
+            }
+          }
+        }
+      }
+    }
+    cluster_sync_all();                                    // nobody leaves while its smem may still be read
+  }
+  if (grp > 0) return;
 
-  // ---- epilogue
+  // ---- epilogue on the owned units
   const int co = co0 + ty * 8;
   if (co >= P.Cout) return;
-  float add[8];
-#pragma unroll
-  for (int n = 0; n < 8; ++n) {
-    float v = 0.f;
-    if (co + n < P.Cout) {
-      v = P.bias[co + n];
-      if (P.cond) v += P.cond[(long)b * P.cond_ld + co + n];
-    }
-    add[n] = v;
-  }
   const bool gate = (P.epi & EPI_GATE) != 0;
   const bool aligned = ((P.ldy | P.yoff) & 3) == 0 && (!P.res || ((P.ldr | P.roff) & 3) == 0);
+  const int climit = gate ? (P.Cout >> 1) : P.Cout;
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
+    if (m < m_lo || m >= m_hi) continue;
     const int t = t0 + tx + 16 * m;
     if (t >= L) continue;
     const long orow = out_base + (long)t * P.out_mul + P.out_add;
-    float v[8];
 #pragma unroll
-    for (int n = 0; n < 8; ++n) v[n] = acc[m][n] + add[n];
-    int nout = 8, oc = co;
-    if (gate) {
+    for (int q = 0; q < 2; ++q) {
+      if (q < q_lo || q >= q_hi) continue;
+      const int c4 = co + q * 4;
+      float v[4];
 #pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const float tt = tanhf(v[2 * n]);
-        const float ss = 1.f / (1.f + expf(-v[2 * n + 1]));
-        v[n] = tt * ss;
+      for (int e = 0; e < 4; ++e) {
+        float u = acc[m][q * 4 + e];
+        if (c4 + e < P.Cout) {
+          u += P.bias[c4 + e];
+          if (P.cond) u += P.cond[(long)b * P.cond_ld + c4 + e];
+        }
+        v[e] = u;
       }
-      nout = 4;
-      oc = co >> 1;
-    }
-    const int climit = gate ? (P.Cout >> 1) : P.Cout;
-#pragma unroll
-    for (int n = 0; n < 8; ++n) {
-      if (n < nout) {
-        float u = v[n];
-        if (P.epi & EPI_RELU) u = fmaxf(u, 0.f);
-        if (P.epi & EPI_TANH) u = tanhf(u);
-        v[n] = u * P.alpha;
+      int nout = 4, oc = c4;
+      if (gate) {
+        v[0] = tanhf(v[0]) * (1.f / (1.f + expf(-v[1])));
+        v[1] = tanhf(v[2]) * (1.f / (1.f + expf(-v[3])));
+        nout = 2;
+        oc = c4 >> 1;
       }
-    }
-    float* yrow = P.y + orow * (long)P.ldy + P.yoff + oc;
-    const float* rrow = P.res ? (P.res + orow * (long)P.ldr + P.roff + oc) : nullptr;
-    if (aligned && (oc + nout) <= climit) {
-      for (int n4 = 0; n4 < nout; n4 += 4) {
-        float4 o = make_float4(v[n4], v[n4 + 1], v[n4 + 2], v[n4 + 3]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (e < nout) {
+          float u = v[e];
+          if (P.epi & EPI_RELU) u = fmaxf(u, 0.f);
+          if (P.epi & EPI_TANH) u = tanhf(u);
+          v[e] = u * P.alpha;
+        }
+      }
+      float* yrow = P.y + orow * (long)P.ldy + P.yoff + oc;
+      const float* rrow = P.res ? (P.res + orow * (long)P.ldr + P.roff + oc) : nullptr;
+      if (aligned && !gate && (oc + 4) <= climit) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
         if (rrow) {
-          const float4 r = *reinterpret_cast<const float4*>(rrow + n4);
+          const float4 r = *reinterpret_cast<const float4*>(rrow);
           o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
         }
-        *reinterpret_cast<float4*>(yrow + n4) = o;
+        *reinterpret_cast<float4*>(yrow) = o;
+      } else {
+        for (int e = 0; e < nout; ++e)
+          if (oc + e < climit) yrow[e] = v[e] + (rrow ? rrow[e] : 0.f);
       }
-    } else {
-      for (int n = 0; n < nout; ++n)
-        if (oc + n < climit) yrow[n] = v[n] + (rrow ? rrow[n] : 0.f);
     }
   }
 }
@@ -334,7 +435,12 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
 // with -1e4 before the softmax (:183), whose exp underflows to exactly 0 in fp32.
 // Online softmax over key tiles of 32; 4 warps x 4 query rows per CTA.
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_QT = 16, AT_KT = 32, AT_THREADS = 128;
+constexpr int AT_QT = 8, AT_KT = 32, AT_THREADS = 128, AT_RPW = 2;   // 4 warps x 2 query rows
+
+template <int DPL>
+constexpr int attn_smem_floats(int nrel) {
+  return 4 * AT_KT * (32 * DPL + 4) + AT_QT * 32 * DPL + nrel * 32 * DPL + AT_QT * nrel + AT_QT * AT_KT;
+}
 
 template <int DPL>  // dk = 32*DPL
 __global__ void __launch_bounds__(AT_THREADS)
@@ -342,7 +448,7 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
             const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
             const int* __restrict__ offs) {
   constexpr int DK = 32 * DPL;
-  constexpr int KS = DK + 1;
+  constexpr int KS = DK + 4;              // row pitch: 16B aligned (cp.async / LDS.128), conflict-free for both access patterns
   const int b = blockIdx.z, head = blockIdx.y;
   const int len = lens[b];
   const int q0 = blockIdx.x * AT_QT;
@@ -351,15 +457,32 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   const int HT = n_heads * DK;
   const int nrel = 2 * window + 1;
 
-  extern __shared__ float sm[];
-  float* Ks = sm;                         // [KT][KS]
-  float* Vs = Ks + AT_KT * KS;            // [KT][KS]
-  float* Qs = Vs + AT_KT * KS;            // [QT][DK]
-  float* Rv = Qs + AT_QT * DK;            // [nrel][DK]
-  float* QE = Rv + nrel * DK;             // [QT][nrel]
-  float* Ps = QE + AT_QT * nrel;          // [QT][KT]
+  extern __shared__ __align__(16) float sm[];
+  float* KV = sm;                                  // [2 buffers][K | V][KT][KS]
+  float* Qs = KV + 4 * AT_KT * KS;                 // [QT][DK]
+  float* Rv = Qs + AT_QT * DK;                     // [nrel][DK]
+  float* QE = Rv + nrel * DK;                      // [QT][nrel]
+  float* Ps = QE + AT_QT * nrel;                   // [QT][KT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (len + AT_KT - 1) / AT_KT;
+
+  auto issue_tile = [&](int kt) {
+    float* kd = KV + (kt & 1) * 2 * AT_KT * KS;
+    float* vd = kd + AT_KT * KS;
+    const int k0 = kt * AT_KT;
+    for (int i = tid; i < AT_KT * (DK / 4); i += AT_THREADS) {
+      const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+      const int t = k0 + r;
+      const bool ok = t < len;
+      const float* rowp = qkv + (base + (ok ? t : 0)) * (long)ld + head * DK + d4;
+      cp_async16(kd + r * KS + d4, rowp + HT, ok ? 16 : 0);
+      cp_async16(vd + r * KS + d4, rowp + 2 * HT, ok ? 16 : 0);
+    }
+  };
+  issue_tile(0);
+  cp_async_commit();
+
   for (int i = tid; i < AT_QT * DK; i += AT_THREADS) {
     const int r = i / DK, d = i - r * DK;
     const int t = q0 + r;
@@ -367,9 +490,8 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   }
   for (int i = tid; i < nrel * DK; i += AT_THREADS) Rv[i] = relv[i];
   __syncthreads();
-  // q . Ek for the 2W+1 relative offsets
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = warp * 4 + rr;
+  for (int rr = 0; rr < AT_RPW; ++rr) {
+    const int r = warp * AT_RPW + rr;
     for (int m = 0; m < nrel; ++m) {
       float a = 0.f;
 #pragma unroll
@@ -380,45 +502,45 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
     }
   }
 
-  float mrun[4], lrun[4], acc[4][DPL];
+  float mrun[AT_RPW], lrun[AT_RPW], acc[AT_RPW][DPL];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
+  for (int r = 0; r < AT_RPW; ++r) {
     mrun[r] = -INFINITY;
     lrun[r] = 0.f;
 #pragma unroll
     for (int e = 0; e < DPL; ++e) acc[r][e] = 0.f;
   }
 
-  for (int k0 = 0; k0 < len; k0 += AT_KT) {
-    __syncthreads();  // previous tile fully consumed (also orders QE writes before first use)
-    for (int i = tid; i < AT_KT * (DK / 4); i += AT_THREADS) {
-      const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
-      const int t = k0 + r;
-      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-      if (t < len) {
-        const float* rowp = qkv + (base + t) * (long)ld + head * DK + d4;
-        kv = *reinterpret_cast<const float4*>(rowp + HT);
-        vv = *reinterpret_cast<const float4*>(rowp + 2 * HT);
-      }
-      float* kd = Ks + r * KS + d4;
-      float* vd = Vs + r * KS + d4;
-      kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-      vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
-    }
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int k0 = kt * AT_KT;
+    if (kt + 1 < ntiles) issue_tile(kt + 1);     // buffer (kt+1)&1 was consumed in iteration kt-1 (barrier below)
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* Ks = KV + (kt & 1) * 2 * AT_KT * KS;
+    const float* Vs = Ks + AT_KT * KS;
     const int key = k0 + lane;
     const bool kvalid = key < len;
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int d = 0; d < DK; ++d) {
-      const float kd = Ks[lane * KS + d];
+    float s[AT_RPW];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) s[r] = fmaf(Qs[(warp * 4 + r) * DK + d], kd, s[r]);
+    for (int r = 0; r < AT_RPW; ++r) s[r] = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < DK; d4 += 4) {
+      const float4 kd = *reinterpret_cast<const float4*>(Ks + lane * KS + d4);
+#pragma unroll
+      for (int r = 0; r < AT_RPW; ++r) {
+        const float4 qd = *reinterpret_cast<const float4*>(Qs + (warp * AT_RPW + r) * DK + d4);
+        s[r] = fmaf(qd.x, kd.x, s[r]);
+        s[r] = fmaf(qd.y, kd.y, s[r]);
+        s[r] = fmaf(qd.z, kd.z, s[r]);
+        s[r] = fmaf(qd.w, kd.w, s[r]);
+      }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int qi = q0 + warp * 4 + r;
+    for (int r = 0; r < AT_RPW; ++r) {
+      const int qi = q0 + warp * AT_RPW + r;
       const int rel = key - qi + window;
-      if (rel >= 0 && rel < nrel) s[r] += QE[(warp * 4 + r) * nrel + rel];
+      if (rel >= 0 && rel < nrel) s[r] += QE[(warp * AT_RPW + r) * nrel + rel];
       if (!kvalid) s[r] = -INFINITY;
       float mx = s[r];
 #pragma unroll
@@ -433,7 +555,7 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
       mrun[r] = mnew;
 #pragma unroll
       for (int e = 0; e < DPL; ++e) acc[r][e] *= corr;
-      Ps[(warp * 4 + r) * AT_KT + lane] = p;
+      Ps[(warp * AT_RPW + r) * AT_KT + lane] = p;
     }
     __syncwarp();
     const int kmax = min(AT_KT, len - k0);
@@ -442,28 +564,29 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
 #pragma unroll
       for (int e = 0; e < DPL; ++e) vv[e] = Vs[kk * KS + lane + 32 * e];
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const float p = Ps[(warp * 4 + r) * AT_KT + kk];
+      for (int r = 0; r < AT_RPW; ++r) {
+        const float p = Ps[(warp * AT_RPW + r) * AT_KT + kk];
 #pragma unroll
         for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, vv[e], acc[r][e]);
       }
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int qi = q0 + warp * 4 + r;
+    for (int r = 0; r < AT_RPW; ++r) {
+      const int qi = q0 + warp * AT_RPW + r;
       for (int m = 0; m < nrel; ++m) {
         const int kk = qi + m - window - k0;
         if (kk >= 0 && kk < kmax) {
-          const float p = Ps[(warp * 4 + r) * AT_KT + kk];
+          const float p = Ps[(warp * AT_RPW + r) * AT_KT + kk];
 #pragma unroll
           for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, Rv[m * DK + lane + 32 * e], acc[r][e]);
         }
       }
     }
+    __syncthreads();   // tile buffer (kt&1) and Ps fully consumed before the next prefetch overwrites them
   }
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int qi = q0 + warp * 4 + r;
+  for (int r = 0; r < AT_RPW; ++r) {
+    const int qi = q0 + warp * AT_RPW + r;
     if (qi < len) {
       const float inv = 1.f / lrun[r];
 #pragma unroll
@@ -476,7 +599,9 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
 // One DDSConv layer (modules.py:96-108): depthwise dilated conv k -> LN -> GELU(erf) -> 1x1 -> LN ->
 // GELU -> + x.  One CTA = 8 positions x all C channels (C == blockDim.x <= 256).
 // ------------------------------------------------------------------------------------------------
-constexpr int DDS_TT = 8;
+constexpr int DDS_TT = 4;      // positions per CTA
+constexpr int DDS_CH = 32;     // 1x1 weight rows (input channels) per cp.async chunk
+constexpr int DDS_NS = 3;      // chunk ring depth
 
 struct DdsP {
   const float* x;
@@ -528,6 +653,8 @@ __device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, i
   }
 }
 
+// One CTA = DDS_TT positions x all C channels (thread c owns channel c).  The 1x1 weight matrix streams through a
+// 3-deep cp.async ring of 32-row chunks; the first chunks are in flight while the depthwise conv and LN run.
 __global__ void __launch_bounds__(256)
 dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restrict__ offs) {
   const int b = blockIdx.y;
@@ -536,8 +663,25 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
   if (t0 >= len) return;
   const long base = offs[b];
   const int C = P.C, c = threadIdx.x;
-  __shared__ float red[8 * DDS_TT];
-  __shared__ __align__(16) float ys[256 * DDS_TT];  // [ci][tt]
+  extern __shared__ __align__(16) float dsm[];
+  float* Wr = dsm;                                   // [NS][CH][C]
+  float* ys = Wr + DDS_NS * DDS_CH * C;              // [C][TT]
+  float* red = ys + C * DDS_TT;                      // [8][TT]
+  const int nch = C / DDS_CH;
+
+  auto issue_chunk = [&](int ch) {
+    float* dst = Wr + (ch % DDS_NS) * DDS_CH * C;
+    const float* src = P.pw_w + (long)ch * DDS_CH * P.ldw;
+    for (int i = c; i < DDS_CH * (C / 4); i += blockDim.x) {
+      const int r = i / (C / 4), c4 = (i - r * (C / 4)) * 4;
+      cp_async16(dst + r * C + c4, src + (long)r * P.ldw + c4, 16);
+    }
+  };
+#pragma unroll
+  for (int i = 0; i < DDS_NS - 1; ++i) {
+    if (i < nch) issue_chunk(i);
+    cp_async_commit();
+  }
 
   float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
   const int half = (P.k - 1) / 2;
@@ -553,21 +697,30 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
   block_ln_stats(v, red, C, mean, rstd);
   {
     const float g = P.ln1g[c], be = P.ln1b[c];
-#pragma unroll
-    for (int i = 0; i < DDS_TT; ++i) ys[c * DDS_TT + i] = gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
+    float4 o;
+    o.x = gelu_erf((v[0] - mean[0]) * rstd[0] * g + be);
+    o.y = gelu_erf((v[1] - mean[1]) * rstd[1] * g + be);
+    o.z = gelu_erf((v[2] - mean[2]) * rstd[2] * g + be);
+    o.w = gelu_erf((v[3] - mean[3]) * rstd[3] * g + be);
+    *reinterpret_cast<float4*>(ys + c * DDS_TT) = o;
   }
-  __syncthreads();
   {
     const float bias = P.pw_b[c];
 #pragma unroll
     for (int i = 0; i < DDS_TT; ++i) v[i] = bias;
-#pragma unroll 4
-    for (int ci = 0; ci < C; ++ci) {
-      const float w = __ldg(P.pw_w + (long)ci * P.ldw + c);
-      const float4 y0 = *reinterpret_cast<const float4*>(ys + ci * DDS_TT);
-      const float4 y1 = *reinterpret_cast<const float4*>(ys + ci * DDS_TT + 4);
+  }
+  for (int ch = 0; ch < nch; ++ch) {
+    cp_async_wait<DDS_NS - 2>();
+    __syncthreads();                                 // chunk ch landed (and ys visible); slot (ch-1)%NS is free
+    if (ch + DDS_NS - 1 < nch) issue_chunk(ch + DDS_NS - 1);
+    cp_async_commit();
+    const float* wr = Wr + (ch % DDS_NS) * DDS_CH * C + c;
+    const float* yy = ys + ch * DDS_CH * DDS_TT;
+#pragma unroll 8
+    for (int ci = 0; ci < DDS_CH; ++ci) {
+      const float w = wr[ci * C];
+      const float4 y0 = *reinterpret_cast<const float4*>(yy + ci * DDS_TT);
       v[0] = fmaf(w, y0.x, v[0]); v[1] = fmaf(w, y0.y, v[1]); v[2] = fmaf(w, y0.z, v[2]); v[3] = fmaf(w, y0.w, v[3]);
-      v[4] = fmaf(w, y1.x, v[4]); v[5] = fmaf(w, y1.y, v[5]); v[6] = fmaf(w, y1.z, v[6]); v[7] = fmaf(w, y1.w, v[7]);
     }
   }
   block_ln_stats(v, red, C, mean, rstd);
@@ -614,8 +767,16 @@ __device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream, u
   return sqrtf(-2.f * logf(u1)) * cospif(2.f * u2);
 }
 
-__global__ void dp_noise_kernel(const float* __restrict__ eps, int eps_ld, uint64_t seed, float scale, float* __restrict__ za,
+// Per-call scalars live in a small device block so that captured CUDA graphs stay valid across calls:
+//   prm[0] noise_scale, prm[1] length_scale, prm[2] noise_scale_w, prm[4..5] Philox seed (lo, hi as raw bits).
+__device__ __forceinline__ uint64_t prm_seed(const float* prm) {
+  return (uint64_t)__float_as_uint(prm[4]) | ((uint64_t)__float_as_uint(prm[5]) << 32);
+}
+
+__global__ void dp_noise_kernel(const float* __restrict__ eps, int eps_ld, const float* __restrict__ prm, float* __restrict__ za,
                                 float* __restrict__ zb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  const uint64_t seed = prm_seed(prm);
+  const float scale = prm[2];
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lens[b]) return;
@@ -704,7 +865,7 @@ __global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, floa
 //   logw = (z - m) * exp(-logs);  w = exp(logw) * length_scale;  w_ceil = ceil(w);  cum = cumsum(w_ceil)
 // One CTA per utterance; y_len = max(sum, 1).
 // ------------------------------------------------------------------------------------------------
-__global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, float length_scale,
+__global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, const float* __restrict__ prm,
                                 int* __restrict__ wceil, int* __restrict__ cum, int* __restrict__ ylen,
                                 const int* __restrict__ lens, const int* __restrict__ offs) {
   const int b = blockIdx.x;
@@ -712,6 +873,7 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
   const long base = offs[b];
   __shared__ int part[1024];
   __shared__ int carry;
+  const float length_scale = prm[1];
   const float m = ea[ea_ch], nlogs = -ea[ea_n + ea_ch];
   const float es = expf(nlogs);
   if (threadIdx.x == 0) carry = 0;
@@ -743,12 +905,15 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
   if (threadIdx.x == 0) ylen[b] = carry < 1 ? 1 : carry;
 }
 
+// Packed row offsets of the utterances at frame resolution.  SEQ_GAP empty rows separate consecutive utterances
+// (never written, zeroed where a TMA-fed kernel reads them) so that a conv halo can never reach a neighbour.
+constexpr int SEQ_GAP = 8;
 __global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restrict__ yoff, int B) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int o = 0;
     for (int b = 0; b < B; ++b) {
       yoff[b] = o;
-      o += ylen[b];
+      o += ylen[b] + (b + 1 < B ? SEQ_GAP : 0);
     }
     yoff[B] = o;
   }
@@ -762,8 +927,10 @@ __global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restri
 __global__ void sample_prior_kernel(const float* __restrict__ stats, int I, const int* __restrict__ cum,
                                     const int* __restrict__ tok_len, const int* __restrict__ tok_off,
                                     const int* __restrict__ frm_len, const int* __restrict__ frm_off,
-                                    const float* __restrict__ eps, int eps_ld, uint64_t seed, float noise_scale,
+                                    const float* __restrict__ eps, int eps_ld, const float* __restrict__ prm,
                                     float* __restrict__ zp, int* __restrict__ frame_token) {
+  const uint64_t seed = prm_seed(prm);
+  const float noise_scale = prm[0];
   const int b = blockIdx.y;
   const int j = blockIdx.x;
   if (j >= frm_len[b]) return;

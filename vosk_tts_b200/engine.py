@@ -40,7 +40,9 @@ class VttsConfig(C.Structure):
 
 EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "vtts_synthesize",
            "vtts_durations_dev", "vtts_synthesize_dev", "vtts_hop", "vtts_stage_timings",
-           "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read"]
+           "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
+           "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
+           "vtts_profile_read_tc"]
 
 
 def lib_path():
@@ -87,6 +89,16 @@ def load_library(build_if_missing=True):
     lib.vtts_debug_flags.restype = i32
     lib.vtts_debug_read.argtypes = [vp, C.c_char_p, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     lib.vtts_debug_read.restype = i32
+    lib.vtts_set_graphs.argtypes = [vp, i32]
+    lib.vtts_set_graphs.restype = i32
+    lib.vtts_graph_replays.argtypes = [vp]
+    lib.vtts_graph_replays.restype = C.c_uint64
+    lib.vtts_profile.argtypes = [vp, i32]
+    lib.vtts_profile.restype = i32
+    lib.vtts_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    lib.vtts_profile_read.restype = i32
+    lib.vtts_profile_read_tc.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    lib.vtts_profile_read_tc.restype = i32
     _LIB = lib
     return lib
 
@@ -228,6 +240,23 @@ class Engine:
 
     def stream(self):
         return int(self.lib.vtts_stream(self.h) or 0)
+
+    def set_graphs(self, enable):
+        self._check(self.lib.vtts_set_graphs(self.h, int(bool(enable))))
+
+    def graph_replays(self):
+        return int(self.lib.vtts_graph_replays(self.h))
+
+    def profile(self, enable):
+        self._check(self.lib.vtts_profile(self.h, int(bool(enable))))
+
+    def profile_read(self):
+        ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+        self._check(self.lib.vtts_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl)))
+        out = dict(conv_ms=ms.value, conv_launches=int(n.value), conv_flops=fl.value)
+        self._check(self.lib.vtts_profile_read_tc(self.h, C.byref(ms), C.byref(n), C.byref(fl)))
+        out.update(tc_ms=ms.value, tc_launches=int(n.value), tc_flops=fl.value)
+        return out
 
     def debug_flags(self, flags):
         self._check(self.lib.vtts_debug_flags(self.h, int(flags)))

@@ -74,6 +74,17 @@ def pqmf_synthesis_filter(subbands=4, taps=62, cutoff_ratio=0.15, beta=9.0):
     return hs.astype(np.float32)
 
 
+def to_bf16_bits(a):
+    """float32 -> bf16 bit patterns (uint16), round-to-nearest-even like __float2bfloat16_rn."""
+    x = np.ascontiguousarray(a, np.float32).view(np.uint32).astype(np.uint64)
+    r = (x + 0x7FFF + ((x >> 16) & 1)) >> 16
+    return r.astype(np.uint16)
+
+
+def from_bf16_bits(b):
+    return (b.astype(np.uint32) << 16).view(np.float32)
+
+
 class _Packer:
     ALIGN = 64  # floats
 
@@ -110,6 +121,21 @@ class _Packer:
         self.add(name + ".w", wp)
         self.add(name + ".b", bp)
 
+    def conv_tc(self, name, w, co_perm=None, ci_perm=None):
+        """Split-bf16 copy of a conv weight for the tcgen05 path: <name>.th / <name>.tl = [k][Cout][Cin] bf16
+        (K-major rows for TMA), hi = rne_bf16(w), lo = rne_bf16(w - hi); two bf16 per fp32 blob slot."""
+        w = np.asarray(w, np.float32)
+        if co_perm is not None:
+            w = w[co_perm]
+        if ci_perm is not None:
+            w = w[:, ci_perm]
+        wt = np.ascontiguousarray(np.transpose(w, (2, 0, 1)))          # [k][Cout][Cin]
+        hi = to_bf16_bits(wt)
+        lo = to_bf16_bits(wt - from_bf16_bits(hi))
+        assert wt.size % 2 == 0
+        self.add(name + ".th", hi.reshape(-1).view(np.float32))
+        self.add(name + ".tl", lo.reshape(-1).view(np.float32))
+
     def finish(self):
         blob = np.concatenate(self.chunks) if self.chunks else np.zeros(0, np.float32)
         manifest = "".join("%s %d %d\n" % e for e in self.entries)
@@ -131,8 +157,10 @@ def convt_phases(u, K):
     return phases
 
 
-def pack(w, cfg):
-    """w: folded state dict (reference names); returns (blob float32[n], manifest str)."""
+def pack(w, cfg, tc=True):
+    """w: folded state dict (reference names); returns (blob float32[n], manifest str).
+    tc=True also packs split-bf16 copies of the decoder convs for the tcgen05 path (precision mode 1)."""
+    tc = tc and cfg["decoder"] == "mb_istft" and str(cfg["resblock"]) == "1"
     g = lambda k: w[k].detach().cpu().numpy() if hasattr(w[k], "detach") else np.asarray(w[k])
     H, I, G = cfg["hidden_channels"], cfg["inter_channels"], cfg["gin_channels"]
     D = cfg["dp_filter_channels"]
@@ -232,6 +260,8 @@ def pack(w, cfg):
     if nf % 2 == 1:   # odd number of flips leaves the latent channel-reversed: fold into conv_pre
         pre_w = pre_w[:, ::-1].copy()
     P.conv("dec.pre", pre_w, g("dec.conv_pre.bias"))
+    if tc:
+        P.conv_tc("dec.pre", pre_w)
     nk = len(cfg["resblock_kernel_sizes"])
     for i, (u, ku) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
         wt = g("dec.ups.%d.weight" % i)                      # [Cin, Cout, K]
@@ -239,6 +269,8 @@ def pack(w, cfg):
         for r, (pad, js) in enumerate(convt_phases(u, ku)):
             wr = np.stack([wt[:, :, j] for j in js], axis=-1)   # [Cin, Cout, ntaps]
             P.conv("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)), bt)
+            if tc:
+                P.conv_tc("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)))
         for j in range(nk):
             n = i * nk + j
             nd = len(cfg["resblock_dilation_sizes"][j])
@@ -246,10 +278,15 @@ def pack(w, cfg):
                 if cfg["resblock"] == "1":
                     P.conv("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)), g("dec.resblocks.%d.convs1.%d.bias" % (n, d)))
                     P.conv("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)), g("dec.resblocks.%d.convs2.%d.bias" % (n, d)))
+                    if tc:
+                        P.conv_tc("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)))
+                        P.conv_tc("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)))
                 else:
                     P.conv("dec.rb%d.c.%d" % (n, d), g("dec.resblocks.%d.convs.%d.weight" % (n, d)), g("dec.resblocks.%d.convs.%d.bias" % (n, d)))
     if cfg["decoder"] == "mb_istft":
         P.conv("dec.post", g("dec.subband_conv_post.weight"), None)
+        if tc:
+            P.conv_tc("dec.post", g("dec.subband_conv_post.weight"))
         P.add("dec.istft", istft_inverse_basis(cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]))
         P.add("dec.pqmf", pqmf_synthesis_filter(cfg["subbands"]))
     else:
