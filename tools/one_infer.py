@@ -12,7 +12,7 @@ def main():
     cfg = C.DEFAULT_CONFIG
     wl = bench.workload(cfg)
     blob, man = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg)
-    eng = Engine(cfg, blob, man, device=0)
+    eng = Engine(cfg, blob, man, device=0, precision=int(os.environ.get('PRECISION', '0')))
     eng.set_graphs(False)
     for i in range(n):
         t0 = time.perf_counter()

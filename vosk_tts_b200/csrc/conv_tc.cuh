@@ -49,7 +49,14 @@ struct TcBatch {
   TcProblem p[TC_MAXP];
   int n;
   int rmul;
+  unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) for tuning (tools/microbench.py)
 };
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_STAMP(i) do { if (tb.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tb.dbg[i] = gtimer(); } while (0)
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,15 +128,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
 template <int BN>
 constexpr int tc_smem_bytes() {
-  return TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  return TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 }
 
 template <int BN>
@@ -138,6 +139,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   constexpr int A_BYTES = TC_BM * TC_BK * 2;           // 16 KB per plane
   constexpr int B_BYTES = BN * TC_BK * 2;
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  if (threadIdx.x == 0) TC_STAMP(0);
   const int pi = blockIdx.z % tb.n;
   const int b = blockIdx.z / tb.n;
   const TcProblem& P = tb.p[pi];
@@ -155,6 +157,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   uint64_t* empty_bar = full_bar + TC_STAGES;
   uint64_t* tmem_full = empty_bar + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsteps = (P.Cin / TC_BK) * P.k;
@@ -179,6 +182,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) TC_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -195,7 +199,9 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         tma_load_2d(base + A_BYTES, &P.a_lo, c * TC_BK, row, &full_bar[st]);
         tma_load_2d(base + 2 * A_BYTES, &P.w_hi, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
         tma_load_2d(base + 2 * A_BYTES + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
+        if (s == 0) TC_STAMP(2);
       }
+      TC_STAMP(3);
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
@@ -204,6 +210,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
       for (int s = 0; s < nsteps; ++s) {
         const int st = s % TC_STAGES;
         mbar_wait(&full_bar[st], (s / TC_STAGES) & 1);
+        if (s == 0) TC_STAMP(4);
         tc_fence_after();
         const uint32_t abase = smem_u32(smem + st * STAGE_BYTES);
         const uint64_t ahi = umma_desc_sw128(abase), alo = umma_desc_sw128(abase + A_BYTES);
@@ -218,81 +225,123 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         umma_commit(&empty_bar[st]);          // frees the smem stage when these MMAs retire
       }
       umma_commit(tmem_full);                 // accumulator complete
+      TC_STAMP(5);
     }
   } else {
     // ------------------------------------------------------------------ epilogue: 4 warps, one TMEM lane quadrant each
+    // Everything that does not depend on the accumulator is fetched while the mainloop runs: bias (+ per-utterance
+    // conditioning) into shared memory, the residual row into registers.
     const int quad = warp & 3;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
+    const int et = threadIdx.x - 64;                       // 0..127
+    if (et < BN) {
+      const int cc = co0 + et;
+      float bv = 0.f;
+      if (cc < P.Cout) {
+        bv = P.bias[cc];
+        if (P.cond) bv += P.cond[(long)b * P.cond_ld + cc];
+      }
+      bias_s[et] = bv;
+    }
     const int t = t0 + quad * 32 + lane;
     const bool rowok = t < L;
     const long orow = out_base + (long)t * P.out_mul + P.out_add;
     const bool gate = (P.epi & TCE_GATE) != 0;
-#pragma unroll 1
-    for (int n0 = 0; n0 < BN; n0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0, v);
-      const int co = co0 + n0;
-      if (!rowok || co >= P.Cout) continue;
+    const int ocb = gate ? (co0 >> 1) : co0;               // first output channel of this CTA
+    const int nvalid = gate ? min(BN / 2, (P.Cout >> 1) - ocb) : min(BN, P.Cout - co0);   // valid output channels
+    float rr[BN];
+    if (P.res && rowok) {
+      const float* rp = P.res + orow * (long)P.ldr + P.roff + ocb;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (co + i < P.Cout) {
-          float u = v[i] + P.bias[co + i];
-          if (P.cond) u += P.cond[(long)b * P.cond_ld + co + i];
-          v[i] = u;
+      for (int i = 0; i < BN; i += 4) {
+        if (i + 4 <= nvalid) {
+          const float4 q4 = *reinterpret_cast<const float4*>(rp + i);
+          rr[i] = q4.x; rr[i + 1] = q4.y; rr[i + 2] = q4.z; rr[i + 3] = q4.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rr[i + e] = (i + e < nvalid) ? rp[i + e] : 0.f;
         }
       }
-      int nout = 16, oc = co;
+    } else {
+#pragma unroll
+      for (int i = 0; i < BN; ++i) rr[i] = 0.f;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // bias_s visible to the 4 epilogue warps
+    mbar_wait(tmem_full, 0);
+    if (threadIdx.x == 64) TC_STAMP(6);
+    tc_fence_after();
+    float v[BN];
+    {
+      uint32_t rg[BN];
+#pragma unroll
+      for (int n0 = 0; n0 < BN; n0 += 16) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
+              "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
+              "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
+            : "r"(taddr));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < BN; ++i) v[i] = __uint_as_float(rg[i]) + bias_s[i];
+    }
+    if (rowok) {
+      constexpr int NO = BN;                                // outputs per row without gate; BN/2 with gate
       if (gate) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
-        nout = 8;
-        oc = co >> 1;
+        for (int i = 0; i < BN / 2; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
       }
-      const int climit = gate ? (P.Cout >> 1) : P.Cout;
+      const bool relu = (P.epi & TCE_RELU) != 0;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        if (i < nout) {
-          float u = v[i];
-          if (P.epi & TCE_RELU) u = fmaxf(u, 0.f);
-          u *= P.alpha;
-          if (P.res && oc + i < climit) u += P.res[orow * (long)P.ldr + P.roff + oc + i];
-          v[i] = u;
-        }
+      for (int i = 0; i < NO; ++i) {
+        float u = v[i];
+        if (relu) u = fmaxf(u, 0.f);
+        v[i] = u * P.alpha + rr[i];
       }
       if (P.y) {
-        float* yr = P.y + orow * (long)P.ldy + P.yoff + oc;
-        if (oc + nout <= climit && (((P.ldy | P.yoff) & 3) == 0)) {
-          for (int i = 0; i < nout; i += 4) *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-        } else {
-          for (int i = 0; i < nout; ++i)
-            if (oc + i < climit) yr[i] = v[i];
+        float* yr = P.y + orow * (long)P.ldy + P.yoff + ocb;
+        const bool al = ((P.ldy | P.yoff) & 3) == 0;
+#pragma unroll
+        for (int i = 0; i < NO; i += 4) {
+          if (al && i + 4 <= nvalid) {
+            *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (i + e < nvalid) yr[i + e] = v[i + e];
+          }
         }
       }
       if (P.p_hi) {
-        __nv_bfloat16* ph = P.p_hi + orow * (long)P.ldp + P.poff + oc;
-        __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + oc;
-        __align__(16) __nv_bfloat16 hb[16], lb[16];
+        __nv_bfloat16* ph = P.p_hi + orow * (long)P.ldp + P.poff + ocb;
+        __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + ocb;
+        const bool al = ((P.ldp | P.poff) & 7) == 0;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float u = i < nout ? v[i] : 0.f;
-          u = u > 0.f ? u : u * P.pl_slope;
-          split_bf16(u, hb[i], lb[i]);
-        }
-        if (oc + nout <= climit && (((P.ldp | P.poff) & 7) == 0)) {
-          for (int i = 0; i < nout; i += 8) {
-            *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb + i);
-            *reinterpret_cast<uint4*>(pl + i) = *reinterpret_cast<const uint4*>(lb + i);
+        for (int i = 0; i < NO; i += 8) {
+          __align__(16) __nv_bfloat16 hb[8], lb[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float u = v[i + e];
+            u = u > 0.f ? u : u * P.pl_slope;
+            split_bf16(u, hb[e], lb[e]);
           }
-        } else {
-          for (int i = 0; i < nout; ++i)
-            if (oc + i < climit) { ph[i] = hb[i]; pl[i] = lb[i]; }
+          if (al && i + 8 <= nvalid) {
+            *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb);
+            *reinterpret_cast<uint4*>(pl + i) = *reinterpret_cast<const uint4*>(lb);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (i + e < nvalid) { ph[i + e] = hb[e]; pl[i + e] = lb[e]; }
+          }
         }
       }
     }
   }
+  if (threadIdx.x == 64) TC_STAMP(7);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");

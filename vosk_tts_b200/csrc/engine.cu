@@ -52,6 +52,9 @@ struct TcSpec {  // one problem of a grouped tensor-core conv launch
   const float* res = nullptr; int ldr = 0;
   Planes out; float pl_slope = 1.f;
   int out_mul = 1, out_add = 0, in_extra = 0, out_seq_extra = 0;
+  int yoff = 0, roff = 0, epi = 0;
+  float alpha = 1.f;
+  const float* cond = nullptr; int cond_ld = 0;
 };
 struct LnW {
   const float* g = nullptr;
@@ -77,6 +80,8 @@ struct FlowW {
   ConvW pre, post;
   EncLayerW tr;
   std::vector<ConvW> in, rsx, rss;
+  TcW t_qkv, t_o, t_ffn1, t_ffn2, t_post;
+  std::vector<TcW> t_in, t_rsx, t_rss;
 };
 struct UpW {
   std::vector<ConvW> phase;
@@ -147,7 +152,8 @@ struct vtts_engine {
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeFn encode_tiled = nullptr;
-  Buf<__nv_bfloat16> pl_pool[64];       // plane buffers (hi/lo pairs), indexed by the decoder code
+  Buf<__nv_bfloat16> pl_pool[128];            // plane buffers (hi/lo pairs), indexed by the decoder code
+  unsigned long long* tc_dbg = nullptr;     // device stamps buffer (microbench)
   double tc_prof_flops = 0.0;
   uint64_t tc_prof_launches = 0;
   std::vector<cudaEvent_t> tc_prof_ev;
@@ -323,6 +329,7 @@ struct vtts_engine {
     Planes p;
     p.C = C; p.rows = rows;
     const size_t n = (size_t)rows * C + 64;
+    REQUIRE(slot >= 0 && 2 * slot + 1 < 128, VTTS_ERR_INVALID, "plane slot out of range");
     p.hi = ensure(pl_pool[2 * slot], n);
     p.lo = ensure(pl_pool[2 * slot + 1], n);
     if (zero) {     // gap rows between packed utterances must read as zero through TMA
@@ -334,6 +341,8 @@ struct vtts_engine {
   CUtensorMap make_map(const void* base, int C, long rows, int box_rows);
   void launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   void decoder_tc(float* z, const int* fl, const int* fo);
+  void flow_tc(float* z, const int* fl, const int* fo);
+  void launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl);
   void bind_weights();
   void launch_conv(const std::vector<ConvP>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   void encoder_layer(const EncLayerW& L, float*& x, float*& xb, float* qkv, float* ao, float* y, float* ffh, int Hc, int Fc,
@@ -413,6 +422,21 @@ void vtts_engine::bind_weights() {
       F.rss.push_back(conv(p + ".rss" + std::to_string(i), H, H, 1));
     }
     F.post = conv(p + ".post", H, I / 2, 1);
+    if (c.precision == 1 && H % TC_BK == 0) {
+      const int fk = c.flow_kernel_size;
+      if (c.use_transformer_flows) {
+        F.t_qkv = tcw(p + ".tr.qkv", H, 3 * H, 1);
+        F.t_o = tcw(p + ".tr.o", H, H, 1);
+        F.t_ffn1 = tcw(p + ".tr.ffn1", H, H, fk);
+        F.t_ffn2 = tcw(p + ".tr.ffn2", H, H, fk);
+      }
+      for (int i = 0; i < nl; ++i) {
+        F.t_in.push_back(tcw(p + ".in" + std::to_string(i), H, 2 * H, fk));
+        if (i < nl - 1) F.t_rsx.push_back(tcw(p + ".rsx" + std::to_string(i), H, H, 1));
+        F.t_rss.push_back(tcw(p + ".rss" + std::to_string(i), H, H, 1));
+      }
+      F.t_post = tcw(p + ".post", H, I / 2, 1);
+    }
     flow.push_back(F);
   }
   dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7);
@@ -501,18 +525,20 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
     P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN);
     P.bias = q.bias;
-    P.res = q.res; P.ldr = q.ldr;
-    P.y = q.y; P.ldy = q.ldy;
+    P.res = q.res; P.ldr = q.ldr; P.roff = q.roff;
+    P.y = q.y; P.ldy = q.ldy; P.yoff = q.yoff;
+    P.cond = q.cond; P.cond_ld = q.cond_ld; P.epi = q.epi;
     P.p_hi = q.out.hi; P.p_lo = q.out.lo; P.ldp = q.out.C;
     P.Cin = q.Cin; P.Cout = q.Cout; P.k = q.k; P.dil = q.dil; P.pad = q.pad;
     P.out_mul = q.out_mul; P.out_add = q.out_add; P.in_extra = q.in_extra; P.out_seq_extra = q.out_seq_extra;
-    P.alpha = 1.f; P.pl_slope = q.pl_slope;
+    P.alpha = q.alpha; P.pl_slope = q.pl_slope;
     REQUIRE(q.in.C == q.Cin, VTTS_ERR_INVALID, "plane width must equal the conv input channels");
     maxCout = std::max(maxCout, q.Cout);
     maxL = std::max(maxL, maxLen * rmul + q.in_extra);
   }
   tb.n = (int)ps.size();
   tb.rmul = rmul;
+  tb.dbg = tc_dbg;
   dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n);
   if (grid.x == 0) return;
   if (profiling) {
@@ -533,6 +559,98 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     tc_prof_used += 2;
   }
   ++launches;
+}
+
+void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl) {
+  const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
+  dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, B);
+  const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+  __nv_bfloat16* ph = pl ? pl->hi : nullptr;
+  __nv_bfloat16* plo = pl ? pl->lo : nullptr;
+  switch (dk / 32) {
+    case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    case 3: attn_kernel<3><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    default: attn_kernel<4><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+  }
+  CK(cudaGetLastError());
+  ++launches;
+}
+
+// Flow (reverse, models.py:750-757) with every dense conv on the tensor cores.  Producers emit the split-bf16
+// planes their consumer needs: FFMA pre-conv, attention and LayerNorm kernels through an extra epilogue output,
+// tensor-core convs through theirs.  The Flip folding is the same as in the fp32 path.
+void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
+  const vtts_config& c = cfg;
+  const int H = c.hidden_channels, I = c.inter_channels, half = I / 2;
+  const long F = Tfrm;
+  const bool zero = B > 1;
+  const int nf = c.flow_n_flows, nl = c.flow_wn_layers, fk = c.flow_kernel_size;
+  float* h = ensure(d_h, (size_t)F * H);
+  float* h1 = ensure(d_h1, (size_t)F * H);
+  float* wx = ensure(d_wx, (size_t)F * H);
+  float* skip = ensure(d_skip, (size_t)F * H);
+  float* fy = ensure(d_fy, (size_t)F * H);
+  float* fqkv = ensure(d_fqkv, (size_t)F * 3 * H);
+  float* fao = ensure(d_fao, (size_t)F * H);
+  int slot = 40;    // plane slots 40.. are the flow's (the decoder uses 0..)
+  Planes ph = planes(slot++, F, H, zero), pao = planes(slot++, F, H, zero), ph1 = planes(slot++, F, H, zero);
+  Planes pff = planes(slot++, F, H, zero), pwx = planes(slot++, F, H, zero), pacts = planes(slot++, F, H, zero);
+  Planes pskip = planes(slot++, F, H, zero);
+  dim3 lg((maxFrm + 3) / 4, B);
+  for (int f = nf - 1; f >= 0; --f) {
+    const FlowW& W = flow[f];
+    const bool flipped = ((nf - f) % 2) == 1;
+    const int x0off = flipped ? half : 0, x1off = flipped ? 0 : half;
+    {
+      ConvP p = mk(W.pre, z, I, x0off, h, H, 0, 1, 0);
+      Planes& dst = c.use_transformer_flows ? ph : pwx;
+      p.p_hi = dst.hi; p.p_lo = dst.lo; p.ldp = H; p.pl_slope = 1.f;
+      launch_conv({p}, 1, fl, fo, maxFrm, B);
+    }
+    float* wn_x = h;
+    if (c.use_transformer_flows) {
+      { TcSpec q; q.in = ph; q.w = W.t_qkv; q.bias = W.tr.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = fqkv; q.ldy = 3 * H;
+        launch_tc({q}, 1, fl, fo, maxFrm, B); }
+      launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, &pao);
+      { TcSpec q; q.in = pao; q.w = W.t_o; q.bias = W.tr.o.b; q.Cin = H; q.Cout = H; q.y = fy; q.ldy = H;
+        launch_tc({q}, 1, fl, fo, maxFrm, B); }
+      add_ln_kernel<<<lg, 128, 0, stream>>>(h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo);
+      CK(cudaGetLastError());
+      ++launches;
+      { TcSpec q; q.in = ph1; q.w = W.t_ffn1; q.bias = W.tr.ffn1.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
+        q.epi = TCE_RELU; q.out = pff; q.pl_slope = 1.f;
+        launch_tc({q}, 1, fl, fo, maxFrm, B); }
+      { TcSpec q; q.in = pff; q.w = W.t_ffn2; q.bias = W.tr.ffn2.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
+        q.y = fy; q.ldy = H;
+        launch_tc({q}, 1, fl, fo, maxFrm, B); }
+      add_ln_kernel<<<lg, 128, 0, stream>>>(h1, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, pwx.hi, pwx.lo);
+      CK(cudaGetLastError());
+      ++launches;
+      wn_x = wx;
+    }
+    int dil = 1;
+    for (int i = 0; i < nl; ++i) {
+      { TcSpec q; q.in = pwx; q.w = W.t_in[i]; q.bias = W.in[i].b; q.Cin = H; q.Cout = 2 * H; q.k = fk; q.dil = dil;
+        q.pad = dil * (fk - 1) / 2; q.epi = TCE_GATE; q.out = pacts; q.pl_slope = 1.f;
+        if (has_g) { q.cond = d_condv.p + r_flow + (f * nl + i) * 2 * H; q.cond_ld = condR; }
+        launch_tc({q}, 1, fl, fo, maxFrm, B); }
+      TcSpec qs; qs.in = pacts; qs.w = W.t_rss[i]; qs.bias = W.rss[i].b; qs.Cin = H; qs.Cout = H; qs.y = skip; qs.ldy = H;
+      if (i > 0) { qs.res = skip; qs.ldr = H; }
+      if (i < nl - 1) {
+        TcSpec qx; qx.in = pacts; qx.w = W.t_rsx[i]; qx.bias = W.rsx[i].b; qx.Cin = H; qx.Cout = H; qx.y = wn_x; qx.ldy = H;
+        qx.res = wn_x; qx.ldr = H; qx.out = pwx; qx.pl_slope = 1.f;
+        launch_tc({qx, qs}, 1, fl, fo, maxFrm, B);
+      } else {
+        qs.out = pskip; qs.pl_slope = 1.f;
+        launch_tc({qs}, 1, fl, fo, maxFrm, B);
+      }
+      dil *= c.flow_dilation_rate;
+    }
+    { TcSpec q; q.in = pskip; q.w = W.t_post; q.bias = W.post.b; q.Cin = H; q.Cout = half; q.alpha = -1.f;
+      q.y = z; q.ldy = I; q.yoff = x1off; q.res = z; q.ldr = I; q.roff = x1off;
+      launch_tc({q}, 1, fl, fo, maxFrm, B); }
+  }
 }
 
 // Decoder on the tensor cores (models.py:1016-1040): every conv consumes the split-bf16 planes written by its
@@ -1001,7 +1119,9 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
     ffh2 = ensure(d_ffh2, F * H);
   }
   const int nf = c.flow_n_flows, nl = c.flow_wn_layers, fk = c.flow_kernel_size;
-  for (int f = nf - 1; f >= 0; --f) {
+  const bool flow_on_tc = tc && !flow.empty() && !flow[0].t_in.empty();
+  if (flow_on_tc) flow_tc(z, fl, fo);
+  for (int f = nf - 1; f >= 0 && !flow_on_tc; --f) {
     const FlowW& W = flow[f];
     const bool flipped = ((nf - f) % 2) == 1;
     const int x0off = flipped ? half : 0, x1off = flipped ? 0 : half;
@@ -1517,9 +1637,97 @@ int vtts_profile_read_tc(vtts_handle h, double* ms, uint64_t* launches, double* 
   });
 }
 
+// Micro-benchmark of one conv kernel in isolation (back-to-back launches, CUDA events on the engine stream):
+//   what = "tc:<Cin>:<Cout>:<k>:<dil>:<rows>"   tcgen05 kernel (precision mode 1 engines only)
+//          "ffma:<Cin>:<Cout>:<k>:<dil>:<rows>" fp32 FFMA kernel
+// Returns the average milliseconds per launch, or a negative status.  Used by bench.py for the roofline of the
+// dominant kernel timed alone, and by tools/ for tuning.
 float vtts_microbench(vtts_handle h, const char* what, int iters) {
-  (void)h; (void)what; (void)iters;
-  return -1.f;
+  if (!h || !what || iters < 1) return -1.f;
+  float result = -1.f;
+  int rc = guarded(h, [&] {
+    char kind[16] = {0};
+    int Cin = 0, Cout = 0, k = 1, dil = 1, rows = 0;
+    REQUIRE(sscanf(what, "%15[a-z]:%d:%d:%d:%d:%d", kind, &Cin, &Cout, &k, &dil, &rows) == 6, VTTS_ERR_INVALID, "bad microbench spec");
+    REQUIRE(Cin > 0 && Cout > 0 && k > 0 && rows > 0 && Cin % 64 == 0, VTTS_ERR_INVALID, "bad microbench shape");
+    const bool is_tc = strcmp(kind, "tc") == 0;
+    REQUIRE(is_tc || strcmp(kind, "ffma") == 0, VTTS_ERR_INVALID, "unknown microbench kind");
+    REQUIRE(!is_tc || h->tc, VTTS_ERR_INVALID, "tc microbench needs a precision-1 engine");
+    // save state that the launch helpers read
+    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len;
+    h->B = 1; h->h_frm_len.assign(1, rows); h->h_tok_len.assign(1, rows);
+    int* dl = nullptr; int* dof = nullptr; float *x = nullptr, *y = nullptr, *w = nullptr, *bias = nullptr;
+    __nv_bfloat16 *ph = nullptr, *pl = nullptr, *wh = nullptr, *wl = nullptr;
+    const int ldw = (Cout + 3) / 4 * 4;
+    CK(cudaMalloc(&dl, 8)); CK(cudaMalloc(&dof, 8));
+    const int hl[2] = {rows, rows}, ho[2] = {0, rows};
+    CK(cudaMemcpy(dl, hl, 8, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dof, ho, 8, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&y, (size_t)rows * Cout * 4)); CK(cudaMalloc(&bias, (size_t)ldw * 4)); CK(cudaMemset(bias, 0, (size_t)ldw * 4));
+    if (is_tc) {
+      CK(cudaMalloc(&ph, (size_t)rows * Cin * 2)); CK(cudaMalloc(&pl, (size_t)rows * Cin * 2));
+      CK(cudaMalloc(&wh, (size_t)k * Cout * Cin * 2)); CK(cudaMalloc(&wl, (size_t)k * Cout * Cin * 2));
+      CK(cudaMemset(ph, 0, (size_t)rows * Cin * 2)); CK(cudaMemset(pl, 0, (size_t)rows * Cin * 2));
+      CK(cudaMemset(wh, 0, (size_t)k * Cout * Cin * 2)); CK(cudaMemset(wl, 0, (size_t)k * Cout * Cin * 2));
+    } else {
+      CK(cudaMalloc(&x, (size_t)rows * Cin * 4)); CK(cudaMalloc(&w, (size_t)k * Cin * ldw * 4));
+      CK(cudaMemset(x, 0, (size_t)rows * Cin * 4)); CK(cudaMemset(w, 0, (size_t)k * Cin * ldw * 4));
+    }
+    auto once = [&] {
+      if (is_tc) {
+        TcSpec q;
+        q.in.hi = ph; q.in.lo = pl; q.in.C = Cin; q.in.rows = rows;
+        q.w.hi = wh; q.w.lo = wl; q.bias = bias; q.Cin = Cin; q.Cout = Cout; q.k = k; q.dil = dil; q.pad = dil * (k - 1) / 2;
+        q.y = y; q.ldy = Cout;
+        h->launch_tc({q}, 1, dl, dof, rows, 1);
+      } else {
+        ConvW W; W.w = w; W.b = bias; W.Cin = Cin; W.Cout = Cout; W.k = k; W.ldw = ldw;
+        h->launch_conv({mk(W, x, Cin, 0, y, Cout, 0, dil, dil * (k - 1) / 2)}, 1, dl, dof, rows, 1);
+      }
+    };
+    const bool prof0 = h->profiling; h->profiling = false;
+    for (int i = 0; i < 3; ++i) once();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    // the launches are captured into one CUDA graph so that the host launch path is not what gets timed
+    cudaGraph_t graph = nullptr; cudaGraphExec_t gexec = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; ++i) once();
+    CK(cudaStreamEndCapture(h->stream, &graph));
+    CK(cudaGraphInstantiate(&gexec, graph, 0));
+    CK(cudaGraphLaunch(gexec, h->stream));           // warm
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaEventRecord(e0, h->stream));
+    CK(cudaGraphLaunch(gexec, h->stream));
+    CK(cudaEventRecord(e1, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaGraphExecDestroy(gexec); cudaGraphDestroy(graph);
+    if (is_tc && getenv("VTTS_TC_STAMPS")) {
+      unsigned long long* d = nullptr;
+      CK(cudaMalloc(&d, 16 * 8)); CK(cudaMemset(d, 0, 16 * 8));
+      h->tc_dbg = d;
+      cudaEvent_t a0, a1; CK(cudaEventCreate(&a0)); CK(cudaEventCreate(&a1));
+      CK(cudaEventRecord(a0, h->stream));
+      once();
+      CK(cudaEventRecord(a1, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      h->tc_dbg = nullptr;
+      unsigned long long st[16];
+      CK(cudaMemcpy(st, d, sizeof(st), cudaMemcpyDeviceToHost));
+      float one = 0.f; CK(cudaEventElapsedTime(&one, a0, a1));
+      fprintf(stderr, "[tc stamps %s] event %.2f us | entry->setup %.2f | ->first TMA issued %.2f | ->all TMA issued %.2f | ->first full %.2f | ->mma issued %.2f | ->acc ready %.2f | ->epi done %.2f | ->sync %.2f (us since entry)\n",
+              what, one * 1e3, (st[1] - st[0]) / 1e3, (st[2] - st[0]) / 1e3, (st[3] - st[0]) / 1e3, (st[4] - st[0]) / 1e3,
+              (st[5] - st[0]) / 1e3, (st[6] - st[0]) / 1e3, (st[7] - st[0]) / 1e3, (st[8] - st[0]) / 1e3);
+      cudaFree(d); cudaEventDestroy(a0); cudaEventDestroy(a1);
+    }
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    result = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    h->profiling = prof0;
+    for (void* p2 : {(void*)dl, (void*)dof, (void*)x, (void*)y, (void*)w, (void*)bias, (void*)ph, (void*)pl, (void*)wh, (void*)wl}) if (p2) cudaFree(p2);
+    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0;
+  });
+  return rc == VTTS_OK ? result : (float)rc;
 }
 
 }  // extern "C"

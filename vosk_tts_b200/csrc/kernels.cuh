@@ -7,11 +7,18 @@
 // reference's x_mask multiplications (attentions.py:50,298,301; modules.py:96-108,148-176) and the
 // per-utterance zero padding of the unmasked decoder convs (modules.py:210-225 with x_mask=None).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <math.h>
 
 namespace vtts {
+
+// fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative: the operand format of the tensor-core convs
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
 
 // ------------------------------------------------------------------------------------------------
 // Generic grouped conv1d-as-GEMM (direct, im2col-free), fp32 FFMA.
@@ -47,6 +54,10 @@ struct ConvP {
   float slope;
   int epi;
   float alpha;
+  __nv_bfloat16* p_hi;   // optional split-bf16 planes of the output (same rows, `ldp` channels per row) for a
+  __nv_bfloat16* p_lo;   // tensor-core consumer; written as lrelu(out, pl_slope)
+  int ldp;
+  float pl_slope;
 };
 
 struct ConvBatch {
@@ -342,6 +353,18 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
         for (int e = 0; e < nout; ++e)
           if (oc + e < climit) yrow[e] = v[e] + (rrow ? rrow[e] : 0.f);
       }
+      if (P.p_hi) {
+        for (int e = 0; e < nout; ++e) {
+          if (oc + e < climit) {
+            float u = v[e] + (rrow ? rrow[e] : 0.f);
+            u = u > 0.f ? u : u * P.pl_slope;
+            __nv_bfloat16 hb, lb;
+            split_bf16(u, hb, lb);
+            P.p_hi[orow * (long)P.ldp + oc + e] = hb;
+            P.p_lo[orow * (long)P.ldp + oc + e] = lb;
+          }
+        }
+      }
     }
   }
 }
@@ -392,7 +415,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, const float* __restrict__ gamma,
                               const float* __restrict__ beta, const float* __restrict__ cadd, const float* __restrict__ vec,
-                              int vec_ld, float* __restrict__ out, const int* __restrict__ lens, const int* __restrict__ offs, int C) {
+                              int vec_ld, float* __restrict__ out, const int* __restrict__ lens, const int* __restrict__ offs, int C,
+                              __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr) {
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -425,6 +449,12 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
     if (cadd) u += cadd[row * C + c];
     if (vec) u += vec[(long)b * vec_ld + c];
     out[row * C + c] = u;
+    if (p_hi) {
+      __nv_bfloat16 hb, lb;
+      split_bf16(u, hb, lb);
+      p_hi[row * C + c] = hb;
+      p_lo[row * C + c] = lb;
+    }
   }
 }
 
@@ -446,7 +476,7 @@ template <int DPL>  // dk = 32*DPL
 __global__ void __launch_bounds__(AT_THREADS)
 attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
             const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
-            const int* __restrict__ offs) {
+            const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr) {
   constexpr int DK = 32 * DPL;
   constexpr int KS = DK + 4;              // row pitch: 16B aligned (cp.async / LDS.128), conflict-free for both access patterns
   const int b = blockIdx.z, head = blockIdx.y;
@@ -590,7 +620,17 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
     if (qi < len) {
       const float inv = 1.f / lrun[r];
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) out[(base + qi) * (long)ldo + head * DK + lane + 32 * e] = acc[r][e] * inv;
+      for (int e = 0; e < DPL; ++e) {
+        const float o = acc[r][e] * inv;
+        const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
+        out[idx] = o;
+        if (p_hi) {
+          __nv_bfloat16 hb, lb;
+          split_bf16(o, hb, lb);
+          p_hi[idx] = hb;
+          p_lo[idx] = lb;
+        }
+      }
     }
   }
 }

@@ -241,6 +241,12 @@ class Engine:
     def stream(self):
         return int(self.lib.vtts_stream(self.h) or 0)
 
+    def microbench(self, what, iters=50):
+        ms = float(self.lib.vtts_microbench(self.h, what.encode(), int(iters)))
+        if ms < 0:
+            raise VttsError(int(ms), self.lib.vtts_last_error(self.h).decode())
+        return ms
+
     def set_graphs(self, enable):
         self._check(self.lib.vtts_set_graphs(self.h, int(bool(enable))))
 

@@ -170,12 +170,18 @@ def pack(w, cfg, tc=True):
         P.add(dst + ".g", g(src + ".gamma"))
         P.add(dst + ".b", g(src + ".beta"))
 
-    def enc_layer(dst, src, i):
+    def enc_layer(dst, src, i, with_tc=False):
         a = "%s.attn_layers.%d" % (src, i)
         wq = np.concatenate([g(a + ".conv_q.weight"), g(a + ".conv_k.weight"), g(a + ".conv_v.weight")], 0)
         bq = np.concatenate([g(a + ".conv_q.bias"), g(a + ".conv_k.bias"), g(a + ".conv_v.bias")], 0)
         P.conv(dst + ".qkv", wq, bq)
         P.conv(dst + ".o", g(a + ".conv_o.weight"), g(a + ".conv_o.bias"))
+        if with_tc:
+            f_ = "%s.ffn_layers.%d" % (src, i)
+            P.conv_tc(dst + ".qkv", wq)
+            P.conv_tc(dst + ".o", g(a + ".conv_o.weight"))
+            P.conv_tc(dst + ".ffn1", g(f_ + ".conv_1.weight"))
+            P.conv_tc(dst + ".ffn2", g(f_ + ".conv_2.weight"))
         P.add(dst + ".relk", g(a + ".emb_rel_k")[0])
         P.add(dst + ".relv", g(a + ".emb_rel_v")[0])
         ln(dst + ".ln1", "%s.norm_layers_1.%d" % (src, i))
@@ -241,19 +247,28 @@ def pack(w, cfg, tc=True):
         flipped = ((nf - f) % 2) == 1
         P.conv(dst + ".pre", g(src + ".pre.weight"), g(src + ".pre.bias"), ci_perm=rev if flipped else None)
         if cfg["use_transformer_flows"]:
-            enc_layer(dst + ".tr", src + ".pre_transformer", 0)
+            enc_layer(dst + ".tr", src + ".pre_transformer", 0, with_tc=tc)
         nl = cfg["flow_wn_layers"]
         il = np.arange(2 * H).reshape(2, H).T.reshape(-1)
         for i in range(nl):
             P.conv("%s.in%d" % (dst, i), g("%s.enc.in_layers.%d.weight" % (src, i)),
                    g("%s.enc.in_layers.%d.bias" % (src, i)), co_perm=il)
             rw, rb = g("%s.enc.res_skip_layers.%d.weight" % (src, i)), g("%s.enc.res_skip_layers.%d.bias" % (src, i))
+            if tc:
+                P.conv_tc("%s.in%d" % (dst, i), g("%s.enc.in_layers.%d.weight" % (src, i)), co_perm=il)
             if i < nl - 1:
                 P.conv("%s.rsx%d" % (dst, i), rw[:H], rb[:H])
                 P.conv("%s.rss%d" % (dst, i), rw[H:], rb[H:])
+                if tc:
+                    P.conv_tc("%s.rsx%d" % (dst, i), rw[:H])
+                    P.conv_tc("%s.rss%d" % (dst, i), rw[H:])
             else:
                 P.conv("%s.rss%d" % (dst, i), rw, rb)
+                if tc:
+                    P.conv_tc("%s.rss%d" % (dst, i), rw)
         P.conv(dst + ".post", g(src + ".post.weight"), g(src + ".post.bias"), co_perm=rev if flipped else None)
+        if tc:
+            P.conv_tc(dst + ".post", g(src + ".post.weight"), co_perm=rev if flipped else None)
 
     # ---- decoder
     pre_w = g("dec.conv_pre.weight")
