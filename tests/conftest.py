@@ -40,13 +40,15 @@ def packed(folded, cfg):
     return weights.pack(folded, cfg)
 
 
-@pytest.fixture(scope="session")
-def engine(packed, cfg):
+@pytest.fixture(scope="session", params=[0, 1], ids=["fp32-ffma", "tcgen05-split-bf16"])
+def engine(request, packed, cfg):
+    """precision 0: fp32 FFMA kernels everywhere; precision 1: flow + decoder convs on tcgen05 (split-bf16 x3)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from vosk_tts_b200.engine import Engine
-    e = Engine(cfg, packed[0], packed[1], device=0)
+    e = Engine(cfg, packed[0], packed[1], device=0, precision=request.param)
+    e.precision = request.param
     yield e
     e.close()
 

@@ -23,7 +23,8 @@ namespace vtts {
 
 constexpr int TC_BM = 128;        // time rows per CTA (UMMA M)
 constexpr int TC_BK = 64;         // input channels per stage (one 128-byte swizzle atom of bf16)
-constexpr int TC_STAGES = 4;
+constexpr int TC_WST = 4;         // weight-tile ring depth (one tile per k-step)
+constexpr int TC_AST = 3;         // activation-tile ring depth (one tile per channel chunk, or per step when !tall)
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAXP = 4;
 
@@ -49,6 +50,10 @@ struct TcBatch {
   TcProblem p[TC_MAXP];
   int n;
   int rmul;
+  int tall;     // 1: one activation tile of 128 + (k-1)*dil rows per channel chunk, taps address it through row-shifted
+                //    UMMA descriptors; 0: a fresh 128-row tile per (chunk, tap)
+  int a_bytes;  // bytes of one activation plane tile in shared memory (multiple of 1024)
+  int baseoff;  // experiment: fill the descriptor base-offset field for row-shifted tiles
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) for tuning (tools/microbench.py)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -90,9 +95,10 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile whose rows are 128 bytes apart (8-row groups 1024 bytes apart)
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, int use_base_offset = 0) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 16-byte units, bits [0,14)
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7) << 49;   // base offset field (experiment)
   d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for swizzled K-major), bits [16,30)
   d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset between 8-row groups, bits [32,46)
   d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
@@ -129,16 +135,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 }
 
 template <int BN>
-constexpr int tc_smem_bytes() {
-  return TC_STAGES * (2 * TC_BM * TC_BK * 2 + 2 * BN * TC_BK * 2) + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+constexpr int tc_smem_bytes(int a_bytes) {
+  return TC_AST * 2 * a_bytes + TC_WST * 2 * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 }
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
-  constexpr int A_BYTES = TC_BM * TC_BK * 2;           // 16 KB per plane
   constexpr int B_BYTES = BN * TC_BK * 2;
-  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   if (threadIdx.x == 0) TC_STAMP(0);
   const int pi = blockIdx.z % tb.n;
   const int b = blockIdx.z / tb.n;
@@ -150,23 +154,28 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (t0 >= L) return;
   const long in_base = (long)offs[b] * tb.rmul + (long)b * P.in_extra;
   const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
+  const int A_BYTES = tb.a_bytes;
+  const bool tall = tb.tall != 0;
 
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TC_STAGES * STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + TC_STAGES;
-  uint64_t* tmem_full = empty_bar + TC_STAGES;
+  uint8_t* smem_w = smem + TC_AST * 2 * A_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_w + TC_WST * 2 * B_BYTES);
+  uint64_t* a_empty = a_full + TC_AST;
+  uint64_t* w_full = a_empty + TC_AST;
+  uint64_t* w_empty = w_full + TC_WST;
+  uint64_t* tmem_full = w_empty + TC_WST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nsteps = (P.Cin / TC_BK) * P.k;
+  const int a_per = tall ? P.k : 1;                    // k-steps sharing one activation tile
+  const int na = nsteps / a_per;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < TC_WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_hi)) : "memory");
@@ -187,18 +196,24 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      const uint32_t a_tx = 2u * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per tile pair
       for (int s = 0; s < nsteps; ++s) {
-        const int st = s % TC_STAGES;
-        const int use = s / TC_STAGES;
-        if (use > 0) mbar_wait(&empty_bar[st], (use - 1) & 1);
         const int c = s / P.k, j = s - c * P.k;
-        uint8_t* base = smem + st * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[st], STAGE_BYTES);
-        const int row = (int)in_base + t0 + j * P.dil - P.pad;
-        tma_load_2d(base, &P.a_hi, c * TC_BK, row, &full_bar[st]);
-        tma_load_2d(base + A_BYTES, &P.a_lo, c * TC_BK, row, &full_bar[st]);
-        tma_load_2d(base + 2 * A_BYTES, &P.w_hi, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
-        tma_load_2d(base + 2 * A_BYTES + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &full_bar[st]);
+        if (s % a_per == 0) {
+          const int ai = s / a_per, ast = ai % TC_AST, use = ai / TC_AST;
+          if (use > 0) mbar_wait(&a_empty[ast], (use - 1) & 1);
+          uint8_t* ab = smem + ast * 2 * A_BYTES;
+          mbar_expect_tx(&a_full[ast], a_tx);
+          const int row = (int)in_base + t0 - P.pad + (tall ? 0 : j * P.dil);
+          tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
+          tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
+        }
+        const int wst = s % TC_WST, wuse = s / TC_WST;
+        if (wuse > 0) mbar_wait(&w_empty[wst], (wuse - 1) & 1);
+        uint8_t* wb = smem_w + wst * 2 * B_BYTES;
+        mbar_expect_tx(&w_full[wst], 2 * B_BYTES);
+        tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
+        tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
         if (s == 0) TC_STAMP(2);
       }
       TC_STAMP(3);
@@ -208,13 +223,17 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
       for (int s = 0; s < nsteps; ++s) {
-        const int st = s % TC_STAGES;
-        mbar_wait(&full_bar[st], (s / TC_STAGES) & 1);
+        const int c = s / P.k, j = s - c * P.k;
+        const int ai = s / a_per, ast = ai % TC_AST;
+        if (s % a_per == 0) mbar_wait(&a_full[ast], (ai / TC_AST) & 1);
+        const int wst = s % TC_WST;
+        mbar_wait(&w_full[wst], (s / TC_WST) & 1);
         if (s == 0) TC_STAMP(4);
         tc_fence_after();
-        const uint32_t abase = smem_u32(smem + st * STAGE_BYTES);
-        const uint64_t ahi = umma_desc_sw128(abase), alo = umma_desc_sw128(abase + A_BYTES);
-        const uint64_t bhi = umma_desc_sw128(abase + 2 * A_BYTES), blo = umma_desc_sw128(abase + 2 * A_BYTES + B_BYTES);
+        const uint32_t abase = smem_u32(smem + ast * 2 * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
+        const uint32_t wbase = smem_u32(smem_w + wst * 2 * B_BYTES);
+        const uint64_t ahi = umma_desc_sw128(abase, tb.baseoff), alo = umma_desc_sw128(abase + A_BYTES, tb.baseoff);
+        const uint64_t bhi = umma_desc_sw128(wbase), blo = umma_desc_sw128(wbase + B_BYTES);
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 16; ++kk) {
           const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
@@ -222,7 +241,9 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
           umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
         }
-        umma_commit(&empty_bar[st]);          // frees the smem stage when these MMAs retire
+        umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
+        if ((s + 1) % a_per == 0) umma_commit(&a_empty[ast]);  // ... and the activation tile after its last tap
+        (void)c;
       }
       umma_commit(tmem_full);                 // accumulator complete
       TC_STAMP(5);

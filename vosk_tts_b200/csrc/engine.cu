@@ -187,7 +187,7 @@ struct vtts_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false;
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -516,12 +516,23 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   static TcBatch tbs;   // 2.6 KB: keep it off the stack frame of every caller
   TcBatch& tb = tbs;
   memset(&tb, 0, sizeof(tb));
-  int maxCout = 0, maxL = 0;
+  int maxCout = 0, maxL = 0, maxNR = TC_BM;
+  bool tall = tc_tall != 0;
+  for (const TcSpec& q : ps) {
+    const int nr = TC_BM + (q.k - 1) * q.dil;
+    if (nr > 192) tall = false;              // shared-memory budget of the activation ring (and TMA box <= 256)
+    maxNR = std::max(maxNR, nr);
+  }
+  if (!tall) maxNR = TC_BM;
+  tb.tall = tall ? 1 : 0;
+  tb.baseoff = tc_baseoff;
+  tb.a_bytes = (maxNR * 128 + 1023) / 1024 * 1024;
   for (size_t i = 0; i < ps.size(); ++i) {
     const TcSpec& q = ps[i];
     TcProblem& P = tb.p[i];
-    P.a_hi = make_map(q.in.hi, q.in.C, q.in.rows, TC_BM);
-    P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, TC_BM);
+    const int box_rows = tall ? TC_BM + (q.k - 1) * q.dil : TC_BM;
+    P.a_hi = make_map(q.in.hi, q.in.C, q.in.rows, box_rows);
+    P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, box_rows);
     P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
     P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN);
     P.bias = q.bias;
@@ -552,7 +563,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     ++tc_prof_launches;
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
   }
-  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes<BN>(), stream>>>(tb, lens, offs);
+  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes<BN>(tb.a_bytes), stream>>>(tb, lens, offs);
   CK(cudaGetLastError());
   if (profiling) {
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used + 1], stream));
@@ -775,7 +786,12 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   }
   cb.n = (int)ps.size();
   cb.rmul = rmul;
-  int G = conv_max_g;
+  const std::vector<int>& hl0 = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+  long base0 = 0;
+  for (const ConvP& q : ps)
+    for (int b = 0; b < nB; ++b) base0 += (long)((hl0[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
+  // few tiles (batch 1): one 128-thread group per CTA and the k-steps spread over a cluster; many tiles: 4 groups per CTA
+  int G = base0 >= 2 * 148 ? conv_max_g : 1;
   for (const ConvP& q : ps) {
     while (G > 1 && q.Cin % (CV_CK * G) != 0) G >>= 1;
   }
@@ -1371,7 +1387,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>()));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>(24 * 1024)));
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -1388,6 +1404,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_MAXS")) h->conv_max_s = std::max(1, atoi(e));
     if (const char* e = getenv("VTTS_CONV_TARGET")) h->conv_target = std::max(1, atoi(e));
     if (const char* e = getenv("VTTS_CONV_MAXG")) h->conv_max_g = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
+    if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     h->bind_weights();
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
