@@ -230,8 +230,8 @@ def main():
     estream = torch.cuda.ExternalStream(eng.stream(), device=dev)
 
     def step_dev():
-        yl = eng.durations_dev(d_ids.data_ptr(), wl["lens"], d_sid.data_ptr(), 1, 128, wl["scales"], d_eps_dp.data_ptr())
-        eng.synthesize_dev(d_wav.data_ptr(), Ty * hop, d_eps_z.data_ptr(), Ty)
+        yl = eng.infer_dev(d_ids.data_ptr(), wl["lens"], d_sid.data_ptr(), 1, 128, wl["scales"], d_wav.data_ptr(), Ty * hop,
+                           d_eps_dp.data_ptr(), d_eps_z.data_ptr(), Ty)
         return int(yl[0])
 
     def barrier():
@@ -279,7 +279,7 @@ def main():
     # ---- e2e through the reference-facing call with host buffers
     feeds = {"input": wl["tok"], "input_lengths": wl["lens"], "scales": wl["scales"], "sid": wl["sid"], "bert": None,
              "phone_duration_extra": None}
-    noise = {"dp": wl["eps_dp"], "z": (lambda mf: wl["eps_z"][:, :, :mf])}
+    noise = {"dp": wl["eps_dp"], "z": np.ascontiguousarray(wl["eps_z"][:, :, :Ty])}
     for _ in range(3):
         sess.run(None, feeds, noise=noise)
     e2e_t = []

@@ -103,6 +103,17 @@ int vtts_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengt
                        int64_t* y_lengths_host);
 int vtts_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld);
 
+/* Both phases in one call (== one InferenceSession.run).  The caller provides capacity instead of exact sizes:
+ * z_ld columns of noise_z (if given) and wav_ld samples per utterance; VTTS_ERR_CAPACITY is returned after phase 1
+ * (y_lengths filled in, durations kept) when they are too small, and vtts_synthesize can then be called with
+ * larger buffers. */
+int vtts_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
+               const float* scales, const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed,
+               int64_t* y_lengths, float* wav, int64_t wav_ld, int32_t* frame_token, int idx_ld);
+int vtts_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                   const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
+                   int64_t* y_lengths_host, float* d_wav, int64_t wav_ld);
+
 /* Samples produced per latent frame (256 for the reference config). */
 int vtts_hop(vtts_handle h);
 /* CUDA-event time (ms) of each stage of the last call: [0] encoder, [1] duration predictor +
@@ -127,6 +138,10 @@ int vtts_profile(vtts_handle h, int enable);
 int vtts_profile_read(vtts_handle h, double* conv_ms, uint64_t* conv_launches, double* conv_flops);
 /* Same counters for the tcgen05 conv kernel (precision mode 1). */
 int vtts_profile_read_tc(vtts_handle h, double* ms, uint64_t* launches, double* flops);
+
+/* In-graph timeline for tuning: enable=1 arms it, enable=0 disarms, enable=2 reads up to max_pairs (source line,
+ * %globaltimer ns) pairs -- one per kernel launch, stamped by the kernel's first CTA at entry. */
+int vtts_timeline(vtts_handle h, int enable, unsigned long long* out, size_t max_pairs, size_t* n_out);
 
 /* Test hooks: flags bit0 keeps a copy of z_p (models.py:1700); vtts_debug_read copies a named workspace
  * tensor of the last call ("x", "stats", "dx", "za", "zb", "condv", "z_p", "z", "d0", "stage<i>", "post") to

@@ -40,7 +40,7 @@ def packed(folded, cfg):
     return weights.pack(folded, cfg)
 
 
-@pytest.fixture(scope="session", params=[0, 1], ids=["fp32-ffma", "tcgen05-split-bf16"])
+@pytest.fixture(scope="session", params=[0, 1, 2], ids=["fp32-ffma", "tcgen05-flow-decoder", "tcgen05-all"])
 def engine(request, packed, cfg):
     """precision 0: fp32 FFMA kernels everywhere; precision 1: flow + decoder convs on tcgen05 (split-bf16 x3)."""
     import torch

@@ -64,27 +64,6 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define TC_STAMP(i) do { if (tb.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) tb.dbg[i] = gtimer(); } while (0)
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
@@ -143,17 +122,14 @@ template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
   constexpr int B_BYTES = BN * TC_BK * 2;
+  PDL_LAUNCH();
   if (threadIdx.x == 0) TC_STAMP(0);
   const int pi = blockIdx.z % tb.n;
   const int b = blockIdx.z / tb.n;
   const TcProblem& P = tb.p[pi];
   const int co0 = blockIdx.y * BN;
   if (co0 >= P.Cout) return;
-  const int L = lens[b] * tb.rmul + P.in_extra;
   const int t0 = blockIdx.x * TC_BM;
-  if (t0 >= L) return;
-  const long in_base = (long)offs[b] * tb.rmul + (long)b * P.in_extra;
-  const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
   const int A_BYTES = tb.a_bytes;
   const bool tall = tb.tall != 0;
 
@@ -191,9 +167,17 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only this CTA's resources; from here on the producer kernel's results are needed
+  PDL_WAIT();
+  const int L = lens[b] * tb.rmul + P.in_extra;
+  const bool active = t0 < L;            // an idle CTA still has to release its TMEM columns below
+  const long in_base = (long)offs[b] * tb.rmul + (long)b * P.in_extra;
+  const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
   if (threadIdx.x == 0) TC_STAMP(1);
 
-  if (warp == 0) {
+  if (!active) {
+    // nothing to compute
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t a_tx = 2u * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per tile pair
@@ -376,6 +360,8 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
 __global__ void split_planes_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                                     int ldp, int C, float slope, int reflect, int rmul, const int* __restrict__ lens,
                                     const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int Lphys = lens[b] * rmul;
   const int L = Lphys + (reflect ? 1 : 0);
@@ -404,6 +390,8 @@ __global__ void split_planes_kernel(const float* __restrict__ x, int ldx, __nv_b
 __global__ void mrf_mean_planes_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c3, int n,
                                        float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C,
                                        float slope, int reflect, int rmul, const int* __restrict__ lens, const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int Lphys = lens[b] * rmul;
   const int L = Lphys + (reflect ? 1 : 0);

@@ -62,6 +62,7 @@ struct LnW {
 };
 struct EncLayerW {
   ConvW qkv, o, ffn1, ffn2;
+  TcW t_qkv, t_o, t_ffn1, t_ffn2;
   LnW ln1, ln2;
   const float* relk = nullptr;
   const float* relv = nullptr;
@@ -147,7 +148,8 @@ struct vtts_engine {
   std::vector<RbW> rbs;
   int hop = 0, up_total = 1;
   bool tc = false;                      // precision mode 1: tcgen05 path for the decoder convs
-  TcW tc_pre, tc_post;
+  TcW tc_pre, tc_post, tc_encproj;
+  bool enc_on_tc = false;               // precision mode 2: the text encoder's convs on tcgen05 as well
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -186,7 +188,7 @@ struct vtts_engine {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
-  bool capturing = false, use_graphs = true, last_graphed = false;
+  bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = false;   // PDL measured slower inside graphs
   int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
@@ -269,13 +271,32 @@ struct vtts_engine {
       if (okey != key) { if (graphs[okey].exec) cudaGraphExecDestroy(graphs[okey].exec); graphs.erase(okey); }
     }
   }
+  // Every kernel goes through here: programmatic dependent launch lets the next kernel's prologue overlap this one's tail.
+  template <typename... KArgs, typename... Args>
+  void klaunch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = use_pdl ? 1 : 0;
+    CK(cudaLaunchKernelEx(&lc, kern, static_cast<KArgs>(args)...));
+  }
   static uint64_t mix(uint64_t h, uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); return h; }
 
   Tensor tensor(const std::string& name) {
     auto it = tensors.find(name);
     if (it == tensors.end()) throw Err{VTTS_ERR_WEIGHTS, "weight blob has no tensor '" + name + "'"};
+    looked_up.push_back(name);
     return it->second;
   }
+  std::vector<std::string> looked_up;          // tensors the engine bound, in first-use order
+  Buf<PrefRange> d_pref;                       // L2 prefetch list for this precision mode
+  int n_pref = 0, n_pref_phase1 = 0;
+  bool use_prefetch = false;                   // measured: no gain on B200 (weights are not the latency bottleneck)
+  void build_prefetch_list();
   const float* vec(const std::string& name, size_t n) {
     Tensor t = tensor(name);
     if (t.n != n) {
@@ -372,6 +393,37 @@ ConvP mk(const ConvW& W, const float* x, int ldx, int xoff, float* y, int ldy, i
 
 }  // namespace
 
+// Which bound tensors does a call actually read in this precision mode?  (fp32 `.w` copies of convs that run on
+// tcgen05 are skipped, and so are the bf16 `.th/.tl` copies of convs that stay on the FFMA pipe.)
+void vtts_engine::build_prefetch_list() {
+  auto on_tc = [&](const std::string& nm) {
+    if (nm.rfind("enc.", 0) == 0) return cfg.precision == 2;
+    if (nm.rfind("flow.", 0) == 0 || nm.rfind("dec.", 0) == 0) return cfg.precision >= 1;
+    return false;
+  };
+  std::vector<PrefRange> p1, p2;
+  std::unordered_map<std::string, bool> seen;
+  for (const std::string& nm : looked_up) {
+    if (seen[nm]) continue;
+    seen[nm] = true;
+    const bool is_w = nm.size() > 2 && nm.compare(nm.size() - 2, 2, ".w") == 0;
+    const bool is_t = nm.size() > 3 && (nm.compare(nm.size() - 3, 3, ".th") == 0 || nm.compare(nm.size() - 3, 3, ".tl") == 0);
+    if (is_w && tensors.count(nm.substr(0, nm.size() - 2) + ".th") && on_tc(nm)) continue;
+    if (is_t && !on_tc(nm)) continue;
+    if (nm == "emb_g") continue;                 // one row is read
+    const Tensor& t = tensors[nm];
+    PrefRange r{reinterpret_cast<const char*>(t.p), (unsigned long long)t.n * sizeof(float)};
+    const bool phase1 = nm.rfind("enc.", 0) == 0 || nm.rfind("dp.", 0) == 0 || nm.rfind("cond.", 0) == 0;
+    (phase1 ? p1 : p2).push_back(r);
+  }
+  n_pref_phase1 = (int)p1.size();
+  p1.insert(p1.end(), p2.begin(), p2.end());
+  n_pref = (int)p1.size();
+  PrefRange* d = ensure(d_pref, p1.size() + 1);
+  CK(cudaMemcpyAsync(d, p1.data(), p1.size() * sizeof(PrefRange), cudaMemcpyHostToDevice, stream));
+  CK(cudaStreamSynchronize(stream));
+}
+
 void vtts_engine::bind_weights() {
   const vtts_config& c = cfg;
   const int H = c.hidden_channels, I = c.inter_channels, G = c.gin_channels, D = c.dp_filter_channels;
@@ -396,6 +448,17 @@ void vtts_engine::bind_weights() {
   enc.clear();
   for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size));
   enc_proj = conv("enc.proj", H, 2 * I, 1);
+  enc_on_tc = c.precision == 2 && H % TC_BK == 0 && c.filter_channels % TC_BK == 0;
+  if (enc_on_tc) {
+    for (int i = 0; i < c.n_layers; ++i) {
+      const std::string p = "enc." + std::to_string(i);
+      enc[i].t_qkv = tcw(p + ".qkv", H, 3 * H, 1);
+      enc[i].t_o = tcw(p + ".o", H, H, 1);
+      enc[i].t_ffn1 = tcw(p + ".ffn1", H, c.filter_channels, c.kernel_size);
+      enc[i].t_ffn2 = tcw(p + ".ffn2", c.filter_channels, H, c.kernel_size);
+    }
+    tc_encproj = tcw("enc.proj", H, 2 * I, 1);
+  }
   dp_pre = conv("dp.pre", H, D, 1);
   dp_proj = conv("dp.proj", D, D, 1);
   for (int i = 0; i < 3; ++i) dp_dds[i] = dds("dp.convs." + std::to_string(i), D, c.dp_kernel_size);
@@ -422,7 +485,7 @@ void vtts_engine::bind_weights() {
       F.rss.push_back(conv(p + ".rss" + std::to_string(i), H, H, 1));
     }
     F.post = conv(p + ".post", H, I / 2, 1);
-    if (c.precision == 1 && H % TC_BK == 0) {
+    if (c.precision >= 1 && H % TC_BK == 0) {
       const int fk = c.flow_kernel_size;
       if (c.use_transformer_flows) {
         F.t_qkv = tcw(p + ".tr.qkv", H, 3 * H, 1);
@@ -440,7 +503,7 @@ void vtts_engine::bind_weights() {
     flow.push_back(F);
   }
   dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7);
-  tc = c.precision == 1;
+  tc = c.precision == 1 || c.precision == 2;
   if (tc) {
     REQUIRE(c.decoder_type == 0 && c.resblock_type == 1, VTTS_ERR_INVALID, "tensor-core mode supports the MB-iSTFT / ResBlock1 decoder");
     tc_pre = tcw("dec.pre", I, c.upsample_initial_channel, 7);
@@ -559,11 +622,12 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
       CK(cudaEventCreate(&tc_prof_ev[tc_prof_used + 1]));
     }
     for (const TcSpec& q : ps)
-      for (int b = 0; b < nB; ++b) tc_prof_flops += 2.0 * ((double)h_frm_len[b] * rmul + q.in_extra) * q.Cout * q.Cin * q.k;
+      for (int b = 0; b < nB; ++b)
+        tc_prof_flops += 2.0 * ((double)((lens == d_tok_len.p) ? h_tok_len[b] : h_frm_len[b]) * rmul + q.in_extra) * q.Cout * q.Cin * q.k;
     ++tc_prof_launches;
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
   }
-  conv_tc_kernel<BN><<<grid, TC_THREADS, tc_smem_bytes<BN>(tb.a_bytes), stream>>>(tb, lens, offs);
+  klaunch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes<BN>(tb.a_bytes)), tb, lens, offs);
   CK(cudaGetLastError());
   if (profiling) {
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used + 1], stream));
@@ -575,14 +639,14 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
 void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl) {
   const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
   dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, B);
-  const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+  const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
   __nv_bfloat16* ph = pl ? pl->hi : nullptr;
   __nv_bfloat16* plo = pl ? pl->lo : nullptr;
   switch (dk / 32) {
-    case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    case 3: attn_kernel<3><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    default: attn_kernel<4><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+    default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
   }
   CK(cudaGetLastError());
   ++launches;
@@ -626,7 +690,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
       launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, &pao);
       { TcSpec q; q.in = pao; q.w = W.t_o; q.bias = W.tr.o.b; q.Cin = H; q.Cout = H; q.y = fy; q.ldy = H;
         launch_tc({q}, 1, fl, fo, maxFrm, B); }
-      add_ln_kernel<<<lg, 128, 0, stream>>>(h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo);
       CK(cudaGetLastError());
       ++launches;
       { TcSpec q; q.in = ph1; q.w = W.t_ffn1; q.bias = W.tr.ffn1.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
@@ -635,7 +699,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
       { TcSpec q; q.in = pff; q.w = W.t_ffn2; q.bias = W.tr.ffn2.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
         q.y = fy; q.ldy = H;
         launch_tc({q}, 1, fl, fo, maxFrm, B); }
-      add_ln_kernel<<<lg, 128, 0, stream>>>(h1, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, pwx.hi, pwx.lo);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h1, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, pwx.hi, pwx.lo);
       CK(cudaGetLastError());
       ++launches;
       wn_x = wx;
@@ -676,7 +740,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
   Planes pz = planes(slot++, F, I, zero);
   {
     dim3 g(maxFrm, B);
-    split_planes_kernel<<<g, 64, 0, stream>>>(z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
+    klaunch(split_planes_kernel, dim3(g), dim3(64), (size_t)(0), z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -744,7 +808,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
     Planes nxt = planes(slot++, rows + (last ? B : 0), ch, zero);
     {
       dim3 g(maxFrm * rm + (last ? 1 : 0), B);
-      mrf_mean_planes_kernel<<<g, 32, 0, stream>>>(xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
+      klaunch(mrf_mean_planes_kernel, dim3(g), dim3(32), (size_t)(0), xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
                                                    (debug_flags & 1) ? X : nullptr, nxt.hi, nxt.lo, ch, last ? 0.01f : 0.1f,
                                                    last ? 1 : 0, rm, fl, fo);
       CK(cudaGetLastError());
@@ -767,7 +831,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
   dim3 g((M + TL_M - 1) / TL_M, B);
   const size_t smem = ((size_t)(TL_M / 4 + 16) * pc + (size_t)c.subbands * (TL_M + 2 * (62 / 2 / c.subbands + 1))) * sizeof(float);
   REQUIRE(c.istft_hop == 4 && c.istft_n_fft == 16, VTTS_ERR_INVALID, "iSTFT tail kernel is sized for n_fft=16, hop=4");
-  istft_pqmf_kernel<<<g, TL_THREADS, smem, stream>>>(post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
+  klaunch(istft_pqmf_kernel, dim3(g), dim3(TL_THREADS), (size_t)(smem), post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
   CK(cudaGetLastError());
   ++launches;
 }
@@ -833,13 +897,22 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
     lc.blockDim = dim3(CV_THREADS * G);
     lc.dynamicSmemBytes = smem;
     lc.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = S;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (S > 1) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = S;
+      at[na].val.clusterDim.y = 1;
+      at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (use_pdl) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     lc.attrs = at;
-    lc.numAttrs = S > 1 ? 1 : 0;
+    lc.numAttrs = na;
     switch (G) {
       case 4: CK(cudaLaunchKernelEx(&lc, conv_kernel<4>, cb, lens, offs)); break;
       case 2: CK(cudaLaunchKernelEx(&lc, conv_kernel<2>, cb, lens, offs)); break;
@@ -863,19 +936,19 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
   {
     const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
     dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, nB);
-    const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+    const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
     switch (dk / 32) {
-      case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
-      case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
-      case 3: attn_kernel<3><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
-      default: attn_kernel<4><<<grid, AT_THREADS, smem, stream>>>(qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs); break;
+      case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+      case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+      case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+      default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
     }
     CK(cudaGetLastError());
     ++launches;
   }
   launch_conv({mk(L.o, ao, Hc, 0, y, Hc, 0, 1, 0)}, 1, lens, offs, maxLen, nB);
   dim3 lg((maxLen + 3) / 4, nB);
-  add_ln_kernel<<<lg, 128, 0, stream>>>(x, y, L.ln1.g, L.ln1.b, nullptr, nullptr, 0, xb, lens, offs, Hc);
+  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), x, y, L.ln1.g, L.ln1.b, nullptr, nullptr, 0, xb, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
   CK(cudaGetLastError());
   ++launches;
   {
@@ -884,7 +957,7 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
     launch_conv({p}, 1, lens, offs, maxLen, nB);
   }
   launch_conv({mk(L.ffn2, ffh, Fc, 0, y, Hc, 0, 1, (ks - 1) / 2)}, 1, lens, offs, maxLen, nB);
-  add_ln_kernel<<<lg, 128, 0, stream>>>(xb, y, L.ln2.g, L.ln2.b, cadd_after, vec_after, vec_ld, x, lens, offs, Hc);
+  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb, y, L.ln2.g, L.ln2.b, cadd_after, vec_after, vec_ld, x, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
   CK(cudaGetLastError());
   ++launches;
 }
@@ -901,7 +974,7 @@ void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, c
     P.C = C; P.k = k; P.dil = dil;
     dim3 grid((maxLen + DDS_TT - 1) / DDS_TT, B);
     const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * DDS_TT + 8 * DDS_TT) * sizeof(float);
-    dds_layer_kernel<<<grid, C, smem, stream>>>(P, lens, offs);
+    klaunch(dds_layer_kernel, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
     CK(cudaGetLastError());
     ++launches;
     std::swap(a, b);
@@ -934,9 +1007,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
       CK(cudaMemcpyAsync(sid, pp.sid, B * sizeof(int), cudaMemcpyHostToDevice, stream));
     } else {
       dim3 g((maxTok + 127) / 128, B);
-      pack_ids_kernel<<<g, 128, 0, stream>>>(d_ids64, t_max, ids, tl, to);
+      klaunch(pack_ids_kernel, dim3(g), dim3(128), (size_t)(0), d_ids64, t_max, ids, tl, to);
       CK(cudaGetLastError());
-      cast_sid_kernel<<<(B + 127) / 128, 128, 0, stream>>>(d_sid64, sid, B);
+      klaunch(cast_sid_kernel, dim3((B + 127) / 128), dim3(128), (size_t)(0), d_sid64, sid, B);
       CK(cudaGetLastError());
       launches += 2;
     }
@@ -948,12 +1021,18 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   }
   if (!capturing) CK(cudaEventRecord(ev[1], stream));
 
+  if (use_prefetch && n_pref > 0) {
+    // encoder / duration-predictor weights first, then flow + decoder (needed ~1 ms later)
+    klaunch(l2_prefetch_kernel, dim3(8, 64), dim3(256), (size_t)0, (const PrefRange*)d_pref.p, n_pref, 0, n_pref_phase1);
+    klaunch(l2_prefetch_kernel, dim3(8, 64), dim3(256), (size_t)0, (const PrefRange*)d_pref.p, n_pref, n_pref_phase1, n_pref);
+    launches += 2;
+  }
   // ---- speaker conditioning (models.py:1680-1683)
   float* condv = nullptr;
   if (has_g) {
     condv = ensure(d_condv, (size_t)B * condR);
     dim3 g((condR + 7) / 8, B);
-    cond_kernel<<<g, 256, c.gin_channels * sizeof(float), stream>>>(emb_g, sid, cond_w, cond_b, condv, c.gin_channels, condR, c.n_speakers);
+    klaunch(cond_kernel, dim3(g), dim3(256), (size_t)(c.gin_channels * sizeof(float)), emb_g, sid, cond_w, cond_b, condv, c.gin_channels, condR, c.n_speakers);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -967,18 +1046,51 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   float* y = ensure(d_y, T * H);
   float* ffh = ensure(d_ffh, T * Fc);
   float* stats = ensure(d_stats, T * 2 * I);
+  Planes px, px1, pao, pff;
+  if (enc_on_tc) {
+    const bool zero = B > 1;
+    px = planes(60, (long)T, H, zero); px1 = planes(61, (long)T, H, zero);
+    pao = planes(62, (long)T, H, zero); pff = planes(63, (long)T, Fc, zero);
+  }
   {
     dim3 g(maxTok, B);
-    embed_kernel<<<g, 64, 0, stream>>>(ids, enc_emb, x, tl, to, H, sqrtf((float)H), c.n_vocab,
-                                       (spk_vec && c.cond_layer_idx == 0) ? spk_vec : nullptr, condR);
+    klaunch(embed_kernel, dim3(g), dim3(64), (size_t)(0), ids, enc_emb, x, tl, to, H, sqrtf((float)H), c.n_vocab,
+            (spk_vec && c.cond_layer_idx == 0) ? spk_vec : (const float*)nullptr, condR, px.hi, px.lo);
     CK(cudaGetLastError());
     ++launches;
   }
   for (int i = 0; i < c.n_layers; ++i) {
     const float* va = (spk_vec && c.cond_layer_idx == i + 1) ? spk_vec : nullptr;
-    encoder_layer(enc[i], x, xb, qkv, ao, y, ffh, H, Fc, c.kernel_size, tl, to, maxTok, va, condR, nullptr);
+    if (!enc_on_tc) {
+      encoder_layer(enc[i], x, xb, qkv, ao, y, ffh, H, Fc, c.kernel_size, tl, to, maxTok, va, condR, nullptr);
+      continue;
+    }
+    // precision mode 2: same layer with the four convs on tcgen05 (attentions.py:57-63)
+    const EncLayerW& L = enc[i];
+    const int ks = c.kernel_size;
+    dim3 lg((maxTok + 3) / 4, B);
+    { TcSpec q; q.in = px; q.w = L.t_qkv; q.bias = L.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = qkv; q.ldy = 3 * H;
+      launch_tc({q}, 1, tl, to, maxTok, B); }
+    launch_attn(qkv, ao, L, H, tl, to, maxTok, &pao);
+    { TcSpec q; q.in = pao; q.w = L.t_o; q.bias = L.o.b; q.Cin = H; q.Cout = H; q.y = y; q.ldy = H;
+      launch_tc({q}, 1, tl, to, maxTok, B); }
+    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, x, y, L.ln1.g, L.ln1.b, (const float*)nullptr, (const float*)nullptr, 0, xb, tl, to, H, px1.hi, px1.lo);
+    ++launches;
+    { TcSpec q; q.in = px1; q.w = L.t_ffn1; q.bias = L.ffn1.b; q.Cin = H; q.Cout = Fc; q.k = ks; q.pad = (ks - 1) / 2;
+      q.epi = TCE_RELU; q.out = pff; q.pl_slope = 1.f;
+      launch_tc({q}, 1, tl, to, maxTok, B); }
+    { TcSpec q; q.in = pff; q.w = L.t_ffn2; q.bias = L.ffn2.b; q.Cin = Fc; q.Cout = H; q.k = ks; q.pad = (ks - 1) / 2;
+      q.y = y; q.ldy = H;
+      launch_tc({q}, 1, tl, to, maxTok, B); }
+    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, xb, y, L.ln2.g, L.ln2.b, (const float*)nullptr, va, condR, x, tl, to, H, px.hi, px.lo);
+    ++launches;
   }
-  launch_conv({mk(enc_proj, x, H, 0, stats, 2 * I, 0, 1, 0)}, 1, tl, to, maxTok, B);
+  if (enc_on_tc) {
+    TcSpec q; q.in = px; q.w = tc_encproj; q.bias = enc_proj.b; q.Cin = H; q.Cout = 2 * I; q.y = stats; q.ldy = 2 * I;
+    launch_tc({q}, 1, tl, to, maxTok, B);
+  } else {
+    launch_conv({mk(enc_proj, x, H, 0, stats, 2 * I, 0, 1, 0)}, 1, tl, to, maxTok, B);
+  }
   if (!capturing) CK(cudaEventRecord(ev[2], stream));
 
   // ---- stochastic duration predictor, reverse (models.py:56-63, 93-101)
@@ -1000,7 +1112,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   }
   {
     dim3 g((maxTok + 127) / 128, B);
-    dp_noise_kernel<<<g, 128, 0, stream>>>(noise_dp, t_max, prm, za, zb, tl, to);
+    klaunch(dp_noise_kernel, dim3(g), dim3(128), (size_t)(0), noise_dp, t_max, prm, za, zb, tl, to);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -1012,7 +1124,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     const CfW& F = cf[n - 2];
     {
       dim3 g(maxTok, B);
-      cf_pre_kernel<<<g, 128, 0, stream>>>(cvar, F.pre_w, F.pre_b, dx, dA, tl, to, D);
+      klaunch(cf_pre_kernel, dim3(g), dim3(128), (size_t)(0), cvar, F.pre_w, F.pre_b, dx, dA, tl, to, D);
       CK(cudaGetLastError());
       ++launches;
     }
@@ -1021,7 +1133,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     launch_conv({mk(F.proj, a, D, 0, h29, 32, 0, 1, 0)}, 1, tl, to, maxTok, B);
     {
       dim3 g((maxTok + 127) / 128, B);
-      spline_inverse_kernel<<<g, 128, 0, stream>>>(h29, 32, tvar, nbins, c.dp_tail_bound, sqrtf((float)D), tl, to);
+      klaunch(spline_inverse_kernel, dim3(g), dim3(128), (size_t)(0), h29, 32, tvar, nbins, c.dp_tail_bound, sqrtf((float)D), tl, to);
       CK(cudaGetLastError());
       ++launches;
     }
@@ -1033,9 +1145,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   int* cum = ensure(d_cum, T);
   int* fl = ensure(d_frm_len, B);
   int* fo = ensure(d_frm_off, B + 1);
-  duration_kernel<<<B, 256, 0, stream>>>(zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to);
+  klaunch(duration_kernel, dim3(B), dim3(256), (size_t)(0), zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to);
   CK(cudaGetLastError());
-  frame_offsets_kernel<<<1, 32, 0, stream>>>(fl, fo, B);
+  klaunch(frame_offsets_kernel, dim3(1), dim3(32), (size_t)(0), fl, fo, B);
   CK(cudaGetLastError());
   launches += 2;
   if (!capturing) CK(cudaEventRecord(ev[3], stream));
@@ -1112,7 +1224,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
   int* ftok = ensure(d_ftok, F);
   {
     dim3 g(maxFrm, B);
-    sample_prior_kernel<<<g, 64, 0, stream>>>(d_stats.p, I, d_cum.p, tl, to, fl, fo, noise_z, z_ld, d_prm.p, z, ftok);
+    klaunch(sample_prior_kernel, dim3(g), dim3(64), (size_t)(0), d_stats.p, I, d_cum.p, tl, to, fl, fo, noise_z, z_ld, d_prm.p, z, ftok);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -1152,19 +1264,19 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
       {
         const int dk = H / c.n_heads, nrel = 2 * c.window_size + 1;
         dim3 grid((maxFrm + AT_QT - 1) / AT_QT, c.n_heads, B);
-        const size_t smem = (size_t)(4 * AT_KT * (dk + 4) + AT_QT * dk + nrel * dk + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
+        const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
         switch (dk / 32) {
-          case 1: attn_kernel<1><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
-          case 2: attn_kernel<2><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
-          case 3: attn_kernel<3><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
-          default: attn_kernel<4><<<grid, AT_THREADS, smem, stream>>>(fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo); break;
+          case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+          case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+          case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
+          default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
         }
         CK(cudaGetLastError());
         ++launches;
       }
       launch_conv({mk(W.tr.o, fao, H, 0, fy, H, 0, 1, 0)}, 1, fl, fo, maxFrm, B);
       dim3 lg((maxFrm + 3) / 4, B);
-      add_ln_kernel<<<lg, 128, 0, stream>>>(xa, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, xb2, fl, fo, H);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xa, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, xb2, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       {
@@ -1173,7 +1285,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
         launch_conv({p}, 1, fl, fo, maxFrm, B);
       }
       launch_conv({mk(W.tr.ffn2, ffh2, H, 0, fy, H, 0, 1, (fk - 1) / 2)}, 1, fl, fo, maxFrm, B);
-      add_ln_kernel<<<lg, 128, 0, stream>>>(xb2, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb2, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       wn_in = wx;
@@ -1277,7 +1389,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
     {
       REQUIRE(nk <= 3, VTTS_ERR_INVALID, "more than 3 resblocks per stage not supported");
       const long total4 = (long)(rows * ch / 4);
-      mrf_mean_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr,
+      klaunch(mrf_mean_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), (size_t)(0), xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr,
                                                                            std::min(nk, 3), X, total4);
       CK(cudaGetLastError());
       ++launches;
@@ -1296,7 +1408,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
     dim3 g((M + TL_M - 1) / TL_M, B);
     const size_t smem = ((size_t)(TL_M / 4 + 16) * pc + (size_t)c.subbands * (TL_M + 2 * (62 / 2 / c.subbands + 1))) * sizeof(float);
     REQUIRE(c.istft_hop == 4 && c.istft_n_fft == 16, VTTS_ERR_INVALID, "iSTFT tail kernel is sized for n_fft=16, hop=4");
-    istft_pqmf_kernel<<<g, TL_THREADS, smem, stream>>>(post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
+    klaunch(istft_pqmf_kernel, dim3(g), dim3(TL_THREADS), (size_t)(smem), post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
     CK(cudaGetLastError());
     ++launches;
   } else {
@@ -1369,6 +1481,105 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
 
 }  // namespace
 
+namespace {
+
+static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
+                   const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
+  setup_lengths(h, lengths, B, t_max);
+  memcpy(h->scales, scales, 3 * sizeof(float));
+  h->seed = seed;
+  std::vector<int> packed(h->Ttok), sid32(B);
+  for (int b = 0; b < B; ++b) {
+    for (int t = 0; t < h->h_tok_len[b]; ++t) packed[h->h_tok_off[b] + t] = (int)ids[(size_t)b * t_max + t];
+    sid32[b] = (int)sid[b];
+  }
+  h->stage1(packed.data(), sid32.data(), t_max, noise_dp);
+  uint64_t key = vtts_engine::mix(0x11, (uint64_t)B);
+  key = vtts_engine::mix(key, (uint64_t)t_max);
+  key = vtts_engine::mix(key, noise_dp ? 1 : 0);
+  for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
+  h->run_graphed(key, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
+  h->finish1();
+  for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
+  if (durations) {
+    std::vector<int> wc(h->Ttok);
+    CK(cudaMemcpyAsync(wc.data(), h->d_wceil.p, h->Ttok * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < B; ++b) {
+      for (int t = 0; t < t_max; ++t)
+        durations[(size_t)b * t_max + t] = t < h->h_tok_len[b] ? wc[h->h_tok_off[b] + t] : 0;
+    }
+  }
+}
+
+static void impl_synthesize(vtts_handle h, const float* noise_z, int z_ld, float* wav, int64_t wav_ld, int32_t* frame_token, int idx_ld) {
+  REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize called without vtts_durations");
+  REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+  REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+  REQUIRE(!frame_token || idx_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
+  if (noise_z) {
+    const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
+    char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));   // caller memory may be pageable
+    memcpy(pin, noise_z, n * sizeof(float));
+  }
+  uint64_t key = vtts_engine::mix(0x22, (uint64_t)h->B);
+  key = vtts_engine::mix(key, (uint64_t)z_ld);
+  key = vtts_engine::mix(key, noise_z ? 1 : 0);
+  for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
+  h->run_graphed(key, [&] { h->phase2(noise_z, z_ld, false); });
+  const size_t nw = (size_t)h->Tfrm * h->hop;
+  char* pin = h->ensure_pinned(nw * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
+  float* pw = reinterpret_cast<float*>(pin);
+  int* pi = reinterpret_cast<int*>(pw + nw);
+  CK(cudaMemcpyAsync(pw, h->d_wav.p, nw * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)h->Tfrm * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->ev[7], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  for (int b = 0; b < h->B; ++b) {
+    memcpy(wav + (size_t)b * wav_ld, pw + (size_t)h->h_frm_off[b] * h->hop, (size_t)h->h_frm_len[b] * h->hop * sizeof(float));
+    if (frame_token) memcpy(frame_token + (size_t)b * idx_ld, pi + h->h_frm_off[b], (size_t)h->h_frm_len[b] * sizeof(int));
+  }
+  collect_timings(h);
+  h->have_durations = false;
+}
+
+static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                       const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
+  setup_lengths(h, lengths_host, B, t_max);
+  memcpy(h->scales, scales, 3 * sizeof(float));
+  h->seed = seed;
+  h->stage1(nullptr, nullptr, t_max, nullptr);
+  uint64_t key = vtts_engine::mix(0x33, (uint64_t)B);
+  key = vtts_engine::mix(key, (uint64_t)t_max);
+  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_ids);
+  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_sid);
+  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_dp);
+  for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
+  h->run_graphed(key, [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
+  h->finish1();
+  for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
+}
+
+static void impl_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
+  REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize_dev called without vtts_durations_dev");
+  REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+  REQUIRE(!d_noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+  uint64_t key = vtts_engine::mix(0x44, (uint64_t)h->B);
+  key = vtts_engine::mix(key, (uint64_t)z_ld);
+  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_z);
+  for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
+  h->run_graphed(key, [&] { h->phase2(d_noise_z, z_ld, true); });
+  for (int b = 0; b < h->B; ++b)
+    CK(cudaMemcpyAsync(d_wav + (size_t)b * wav_ld, h->d_wav.p + (size_t)h->h_frm_off[b] * h->hop,
+                       (size_t)h->h_frm_len[b] * h->hop * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  CK(cudaEventRecord(h->ev[7], h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  collect_timings(h);
+  h->have_durations = false;
+}
+
+}  // namespace
+
 extern "C" {
 
 int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, const char* manifest, int blob_is_device,
@@ -1380,8 +1591,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
   h->device = device;
   *out = h;   // returned even on failure so that vtts_last_error() is readable; caller destroys it
   return guarded(h, [&] {
-    REQUIRE(cfg->precision == 0 || cfg->precision == 1, VTTS_ERR_INVALID, "unknown precision mode");
-    if (cfg->precision == 1) {
+    REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, VTTS_ERR_INVALID, "unknown precision mode");
+    if (cfg->precision >= 1) {
       void* fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
@@ -1406,13 +1617,16 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_MAXG")) h->conv_max_g = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
+    if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
+    if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
-    CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    h->build_prefetch_list();
+    CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
@@ -1438,6 +1652,7 @@ void vtts_destroy(vtts_handle h) {
   for (Buf<char>* hb : {&h->h_pin, &h->h_pin_in, &h->h_pin_len, &h->h_pin_z}) if (hb->p) cudaFreeHost(hb->p);
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   fr(h->d_prm.p);
+  fr(h->d_pref.p);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->tc_prof_ev) if (e) cudaEventDestroy(e);
@@ -1451,107 +1666,42 @@ const char* vtts_last_error(vtts_handle h) { return h ? h->err.c_str() : "null h
 int vtts_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
                    const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
   if (!ids || !lengths || !sid || !scales || !y_lengths) return VTTS_ERR_INVALID;
-  return guarded(h, [&] {
-    setup_lengths(h, lengths, B, t_max);
-    memcpy(h->scales, scales, 3 * sizeof(float));
-    h->seed = seed;
-    std::vector<int> packed(h->Ttok), sid32(B);
-    for (int b = 0; b < B; ++b) {
-      for (int t = 0; t < h->h_tok_len[b]; ++t) packed[h->h_tok_off[b] + t] = (int)ids[(size_t)b * t_max + t];
-      sid32[b] = (int)sid[b];
-    }
-    h->stage1(packed.data(), sid32.data(), t_max, noise_dp);
-    uint64_t key = vtts_engine::mix(0x11, (uint64_t)B);
-    key = vtts_engine::mix(key, (uint64_t)t_max);
-    key = vtts_engine::mix(key, noise_dp ? 1 : 0);
-    for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
-    h->run_graphed(key, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
-    h->finish1();
-    for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
-    if (durations) {
-      std::vector<int> wc(h->Ttok);
-      CK(cudaMemcpyAsync(wc.data(), h->d_wceil.p, h->Ttok * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      for (int b = 0; b < B; ++b) {
-        for (int t = 0; t < t_max; ++t)
-          durations[(size_t)b * t_max + t] = t < h->h_tok_len[b] ? wc[h->h_tok_off[b] + t] : 0;
-      }
-    }
-  });
+  return guarded(h, [&] { impl_durations(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, y_lengths, durations); });
 }
 
 int vtts_synthesize(vtts_handle h, const float* noise_z, int z_ld, float* wav, int64_t wav_ld, int32_t* frame_token, int idx_ld) {
   if (!wav) return VTTS_ERR_INVALID;
-  return guarded(h, [&] {
-    REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize called without vtts_durations");
-    REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
-    REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-    REQUIRE(!frame_token || idx_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
-    if (noise_z) {
-      const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
-      char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));   // caller memory may be pageable
-      memcpy(pin, noise_z, n * sizeof(float));
-    }
-    uint64_t key = vtts_engine::mix(0x22, (uint64_t)h->B);
-    key = vtts_engine::mix(key, (uint64_t)z_ld);
-    key = vtts_engine::mix(key, noise_z ? 1 : 0);
-    for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
-    h->run_graphed(key, [&] { h->phase2(noise_z, z_ld, false); });
-    const size_t nw = (size_t)h->Tfrm * h->hop;
-    char* pin = h->ensure_pinned(nw * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
-    float* pw = reinterpret_cast<float*>(pin);
-    int* pi = reinterpret_cast<int*>(pw + nw);
-    CK(cudaMemcpyAsync(pw, h->d_wav.p, nw * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)h->Tfrm * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaEventRecord(h->ev[7], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    for (int b = 0; b < h->B; ++b) {
-      memcpy(wav + (size_t)b * wav_ld, pw + (size_t)h->h_frm_off[b] * h->hop, (size_t)h->h_frm_len[b] * h->hop * sizeof(float));
-      if (frame_token) memcpy(frame_token + (size_t)b * idx_ld, pi + h->h_frm_off[b], (size_t)h->h_frm_len[b] * sizeof(int));
-    }
-    collect_timings(h);
-    h->have_durations = false;
-  });
+  return guarded(h, [&] { impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld); });
 }
 
 int vtts_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
                        const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
   if (!d_ids || !lengths_host || !d_sid || !scales || !y_lengths_host) return VTTS_ERR_INVALID;
-  return guarded(h, [&] {
-    setup_lengths(h, lengths_host, B, t_max);
-    memcpy(h->scales, scales, 3 * sizeof(float));
-    h->seed = seed;
-    h->stage1(nullptr, nullptr, t_max, nullptr);
-    uint64_t key = vtts_engine::mix(0x33, (uint64_t)B);
-    key = vtts_engine::mix(key, (uint64_t)t_max);
-    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_ids);
-    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_sid);
-    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_dp);
-    for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
-    h->run_graphed(key, [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
-    h->finish1();
-    for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
-  });
+  return guarded(h, [&] { impl_durations_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, y_lengths_host); });
 }
 
 int vtts_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
   if (!d_wav) return VTTS_ERR_INVALID;
+  return guarded(h, [&] { impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld); });
+}
+
+int vtts_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max, const float* scales,
+               const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed, int64_t* y_lengths, float* wav, int64_t wav_ld,
+               int32_t* frame_token, int idx_ld) {
+  if (!ids || !lengths || !sid || !scales || !y_lengths || !wav) return VTTS_ERR_INVALID;
   return guarded(h, [&] {
-    REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize_dev called without vtts_durations_dev");
-    REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
-    REQUIRE(!d_noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-    uint64_t key = vtts_engine::mix(0x44, (uint64_t)h->B);
-    key = vtts_engine::mix(key, (uint64_t)z_ld);
-    key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_z);
-    for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
-    h->run_graphed(key, [&] { h->phase2(d_noise_z, z_ld, true); });
-    for (int b = 0; b < h->B; ++b)
-      CK(cudaMemcpyAsync(d_wav + (size_t)b * wav_ld, h->d_wav.p + (size_t)h->h_frm_off[b] * h->hop,
-                         (size_t)h->h_frm_len[b] * h->hop * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
-    CK(cudaEventRecord(h->ev[7], h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    collect_timings(h);
-    h->have_durations = false;
+    impl_durations(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, y_lengths, nullptr);
+    impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld);
+  });
+}
+
+int vtts_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                   const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
+                   int64_t* y_lengths_host, float* d_wav, int64_t wav_ld) {
+  if (!d_ids || !lengths_host || !d_sid || !scales || !y_lengths_host || !d_wav) return VTTS_ERR_INVALID;
+  return guarded(h, [&] {
+    impl_durations_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, y_lengths_host);
+    impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld);
   });
 }
 
@@ -1597,6 +1747,28 @@ int vtts_profile_read(vtts_handle h, double* conv_ms, uint64_t* conv_launches, d
     *conv_ms = ms;
     *conv_launches = h->prof_launches;
     *conv_flops = h->prof_flops;
+  });
+}
+
+// Timeline: enable -> every kernel's first CTA appends (source line, globaltimer) to a device buffer; read returns pairs.
+int vtts_timeline(vtts_handle h, int enable, unsigned long long* out, size_t max_pairs, size_t* n_out) {
+  return guarded(h, [&] {
+    static unsigned long long* d_tl = nullptr;
+    CK(cudaStreamSynchronize(h->stream));
+    if (enable == 1) {
+      if (!d_tl) CK(cudaMalloc(&d_tl, (1 + 2 * 4000) * 8));
+      CK(cudaMemset(d_tl, 0, (1 + 2 * 4000) * 8));
+      CK(cudaMemcpyToSymbol(g_timeline, &d_tl, sizeof(d_tl)));
+    } else if (enable == 0) {
+      unsigned long long* z = nullptr;
+      CK(cudaMemcpyToSymbol(g_timeline, &z, sizeof(z)));
+    } else if (d_tl && out && n_out) {
+      std::vector<unsigned long long> hbuf(1 + 2 * 4000);
+      CK(cudaMemcpy(hbuf.data(), d_tl, hbuf.size() * 8, cudaMemcpyDeviceToHost));
+      size_t n = std::min<size_t>((size_t)hbuf[0], std::min<size_t>(4000, max_pairs));
+      memcpy(out, hbuf.data() + 1, n * 16);
+      *n_out = n;
+    }
   });
 }
 

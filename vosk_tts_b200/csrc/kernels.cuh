@@ -14,6 +14,54 @@
 
 namespace vtts {
 
+// Programmatic dependent launch (PDL): every kernel of the engine is launched with programmatic stream serialisation,
+// so kernel N+1 may start (and run its prologue: barrier init, TMEM allocation, weight prefetch) while kernel N drains.
+// PDL_WAIT() blocks until the predecessor grid has completed and its writes are visible; nothing that a predecessor
+// produces (activations, lens/offs) may be touched, and nothing may be written, before it.  Both are no-ops when the
+// kernel was launched without the attribute.
+// Optional in-graph timeline (tools/timeline.py): CTA (0,0,0) of every kernel appends (source line, %globaltimer) at entry.
+__device__ unsigned long long* g_timeline = nullptr;     // [0] = counter, then pairs (line, ns)
+__device__ __forceinline__ void timeline_stamp(int line) {
+  unsigned long long* tl = g_timeline;
+  if (tl && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(tl, 1ull);
+    if (i < 4000) { tl[1 + 2 * i] = (unsigned long long)line; tl[2 + 2 * i] = t; }
+  }
+}
+#define PDL_LAUNCH() do { timeline_stamp(__LINE__); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+
+// ---- mbarrier / bulk-async-copy wrappers (shared by the tcgen05 conv and the DDS kernel)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine, no tensor map); completion is signalled on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative: the operand format of the tensor-core convs
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
   hi = __float2bfloat16_rn(x);
@@ -107,6 +155,7 @@ __global__ void __launch_bounds__(CV_THREADS * G)
 conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, const int* __restrict__ offs) {
   constexpr int CKS = CV_CK * G;        // channels per step over all groups
   constexpr int NT = CV_THREADS * G;
+  PDL_LAUNCH();
   const int S = cb.S;                   // cluster size along x (1, 2, 4, 8)
   const int rank = S > 1 ? (int)(blockIdx.x % S) : 0;
   const int pi = blockIdx.z % cb.n;
@@ -114,12 +163,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   const ConvP& P = cb.p[pi];
   const int co0 = blockIdx.y * CV_TC;
   if (co0 >= P.Cout) return;            // uniform over the cluster
-  const int Lphys = lens[b] * cb.rmul;
-  const int L = Lphys + P.in_extra;
   const int t0 = (int)(blockIdx.x / S) * CV_TT;
-  if (t0 >= L) return;                  // uniform over the cluster
-  const long in_base = (long)offs[b] * cb.rmul;
-  const long out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
 
   extern __shared__ __align__(16) float smem[];
   const int xw = cb.xw;
@@ -144,6 +188,8 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
     for (int n = 0; n < 8; ++n) acc[m][n] = 0.f;
 
   float4 xr[CV_XR];
+  int Lphys = 0, L = 0;                  // set after PDL_WAIT (lens/offs may come from a predecessor kernel)
+  long in_base = 0, out_base = 0;
 
   auto load_x = [&](int c) {
 #pragma unroll
@@ -198,6 +244,18 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
     }
   };
 
+  // weights are immutable: their first tiles are requested before waiting for the producer of the activations
+#pragma unroll
+  for (int i = 0; i < CV_NS - 1; ++i) {
+    if (i < nmine) issue_w(i);
+    cp_async_commit();
+  }
+  PDL_WAIT();
+  Lphys = lens[b] * cb.rmul;
+  L = Lphys + P.in_extra;
+  if (t0 >= L) return;                  // uniform over the cluster (pending cp.async into our own smem is harmless)
+  in_base = (long)offs[b] * cb.rmul;
+  out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
   int xbuf = 0;        // Xs buffer holding chunk `ccur`
   int ccur = -1;
   if (nmine > 0) {
@@ -205,11 +263,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
     load_x(ccur);
     store_x(0);
   }
-#pragma unroll
-  for (int i = 0; i < CV_NS - 1; ++i) {
-    if (i < nmine) issue_w(i);
-    cp_async_commit();
-  }
+  timeline_stamp(-21);
   for (int i = 0; i < nmine; ++i) {
     const int s = rank + i * S;
     const int c = s / k, j = s - c * k;
@@ -243,6 +297,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   }
 
   // ---- reductions: groups (shared memory) then cluster ranks (distributed shared memory), fixed order
+  timeline_stamp(-22);
   cp_async_wait<0>();
   __syncthreads();
   float* red = smem;                                       // [G-1][32][128]
@@ -286,8 +341,12 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const int idx = (m * 8 + q * 4 + e) * CV_THREADS + ltid;
+              float pr[8];
+#pragma unroll
+              for (int r2 = 0; r2 < 8; ++r2) pr[r2] = r2 < S ? ld_dsmem(part + idx, r2) : 0.f;   // independent loads in flight
               float v = 0.f;
-              for (int r2 = 0; r2 < S; ++r2) v += ld_dsmem(part + idx, r2);
+#pragma unroll
+              for (int r2 = 0; r2 < 8; ++r2) v += pr[r2];                                        // fixed summation order
               acc[m][q * 4 + e] = v;
             }
           }
@@ -297,6 +356,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
     cluster_sync_all();                                    // nobody leaves while its smem may still be read
   }
   if (grp > 0) return;
+  timeline_stamp(-23);
 
   // ---- epilogue on the owned units
   const int co = co0 + ty * 8;
@@ -376,6 +436,8 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
 // ------------------------------------------------------------------------------------------------
 __global__ void cond_kernel(const float* __restrict__ emb_g, const int* __restrict__ sid, const float* __restrict__ W,
                             const float* __restrict__ bias, float* __restrict__ out, int G, int R, int n_speakers) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   extern __shared__ float gs[];
   const int b = blockIdx.y;
   int s = sid[b];
@@ -395,7 +457,10 @@ __global__ void cond_kernel(const float* __restrict__ emb_g, const int* __restri
 // Embedding * sqrt(H) (models.py:318), optional per-utterance vector (cond_layer_idx == 0).
 __global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
                              const int* __restrict__ lens, const int* __restrict__ offs, int H, float scale,
-                             int n_vocab, const float* __restrict__ vec, int vec_ld) {
+                             int n_vocab, const float* __restrict__ vec, int vec_ld, __nv_bfloat16* __restrict__ p_hi,
+                             __nv_bfloat16* __restrict__ p_lo) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int t = blockIdx.x;
   if (t >= lens[b]) return;
@@ -406,6 +471,12 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
     float v = emb[(long)id * H + c] * scale;
     if (vec) v += vec[(long)b * vec_ld + c];
     x[row * H + c] = v;
+    if (p_hi) {
+      __nv_bfloat16 hb, lb;
+      split_bf16(v, hb, lb);
+      p_hi[row * H + c] = hb;
+      p_lo[row * H + c] = lb;
+    }
   }
 }
 
@@ -417,6 +488,8 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
                               const float* __restrict__ beta, const float* __restrict__ cadd, const float* __restrict__ vec,
                               int vec_ld, float* __restrict__ out, const int* __restrict__ lens, const int* __restrict__ offs, int C,
                               __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -465,18 +538,21 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
 // with -1e4 before the softmax (:183), whose exp underflows to exactly 0 in fp32.
 // Online softmax over key tiles of 32; 4 warps x 4 query rows per CTA.
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_QT = 8, AT_KT = 32, AT_THREADS = 128, AT_RPW = 2;   // 4 warps x 2 query rows
+constexpr int AT_QT = 8, AT_KT = 32, AT_THREADS = 256;   // 8 warps, one query row each
+constexpr int AT_NS = 4;                                   // K/V tile ring depth (tiles are latency-, not bandwidth-bound)
 
 template <int DPL>
 constexpr int attn_smem_floats(int nrel) {
-  return 4 * AT_KT * (32 * DPL + 4) + AT_QT * 32 * DPL + nrel * 32 * DPL + AT_QT * nrel + AT_QT * AT_KT;
+  return 2 * AT_NS * AT_KT * (32 * DPL + 4) + AT_QT * (32 * DPL + 4) + 2 * nrel * (32 * DPL + 4) + AT_QT * nrel + AT_QT * AT_KT;
 }
 
 template <int DPL>  // dk = 32*DPL
 __global__ void __launch_bounds__(AT_THREADS)
 attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
             const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
-            const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr) {
+            const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   constexpr int DK = 32 * DPL;
   constexpr int KS = DK + 4;              // row pitch: 16B aligned (cp.async / LDS.128), conflict-free for both access patterns
   const int b = blockIdx.z, head = blockIdx.y;
@@ -488,17 +564,18 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   const int nrel = 2 * window + 1;
 
   extern __shared__ __align__(16) float sm[];
-  float* KV = sm;                                  // [2 buffers][K | V][KT][KS]
-  float* Qs = KV + 4 * AT_KT * KS;                 // [QT][DK]
-  float* Rv = Qs + AT_QT * DK;                     // [nrel][DK]
-  float* QE = Rv + nrel * DK;                      // [QT][nrel]
+  float* KV = sm;                                  // [NS stages][K | V][KT][KS]
+  float* Qs = KV + 2 * AT_NS * AT_KT * KS;         // [QT][KS]
+  float* Rk = Qs + AT_QT * KS;                     // [nrel][KS]
+  float* Rv = Rk + nrel * KS;                      // [nrel][KS]
+  float* QE = Rv + nrel * KS;                      // [QT][nrel]
   float* Ps = QE + AT_QT * nrel;                   // [QT][KT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (len + AT_KT - 1) / AT_KT;
 
   auto issue_tile = [&](int kt) {
-    float* kd = KV + (kt & 1) * 2 * AT_KT * KS;
+    float* kd = KV + (kt % AT_NS) * 2 * AT_KT * KS;
     float* vd = kd + AT_KT * KS;
     const int k0 = kt * AT_KT;
     for (int i = tid; i < AT_KT * (DK / 4); i += AT_THREADS) {
@@ -510,126 +587,130 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
       cp_async16(vd + r * KS + d4, rowp + 2 * HT, ok ? 16 : 0);
     }
   };
-  issue_tile(0);
-  cp_async_commit();
+#pragma unroll
+  for (int i = 0; i < AT_NS - 1; ++i) {
+    if (i < ntiles) issue_tile(i);
+    cp_async_commit();
+  }
 
-  for (int i = tid; i < AT_QT * DK; i += AT_THREADS) {
-    const int r = i / DK, d = i - r * DK;
+  // Q rows (pre-scaled by 1/sqrt(dk) as attentions.py:171 does) and both relative-position tables into shared memory
+  for (int i = tid; i < AT_QT * (DK / 4); i += AT_THREADS) {
+    const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
     const int t = q0 + r;
-    Qs[i] = (t < len) ? (qkv[(base + t) * (long)ld + head * DK + d] / sqrtf((float)DK)) : 0.f;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len) q = *reinterpret_cast<const float4*>(qkv + (base + t) * (long)ld + head * DK + d4);
+    const float sc = sqrtf((float)DK);
+    q.x /= sc; q.y /= sc; q.z /= sc; q.w /= sc;
+    *reinterpret_cast<float4*>(Qs + r * KS + d4) = q;
   }
-  for (int i = tid; i < nrel * DK; i += AT_THREADS) Rv[i] = relv[i];
+  for (int i = tid; i < nrel * (DK / 4); i += AT_THREADS) {
+    const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+    *reinterpret_cast<float4*>(Rk + r * KS + d4) = *reinterpret_cast<const float4*>(relk + r * DK + d4);
+    *reinterpret_cast<float4*>(Rv + r * KS + d4) = *reinterpret_cast<const float4*>(relv + r * DK + d4);
+  }
   __syncthreads();
-  for (int rr = 0; rr < AT_RPW; ++rr) {
-    const int r = warp * AT_RPW + rr;
-    for (int m = 0; m < nrel; ++m) {
-      float a = 0.f;
-#pragma unroll
-      for (int e = 0; e < DPL; ++e) a = fmaf(Qs[r * DK + lane + 32 * e], relk[m * DK + lane + 32 * e], a);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (lane == 0) QE[r * nrel + m] = a;
+  // q . Ek for the 2W+1 relative offsets: one thread per (row, offset)
+  for (int i = tid; i < AT_QT * nrel; i += AT_THREADS) {
+    const int r = i / nrel, m = i - r * nrel;
+    float a = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < DK; d4 += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(Qs + r * KS + d4);
+      const float4 e = *reinterpret_cast<const float4*>(Rk + m * KS + d4);
+      a = fmaf(q.x, e.x, a); a = fmaf(q.y, e.y, a); a = fmaf(q.z, e.z, a); a = fmaf(q.w, e.w, a);
     }
+    QE[i] = a;
   }
+  timeline_stamp(-11);
 
-  float mrun[AT_RPW], lrun[AT_RPW], acc[AT_RPW][DPL];
+  float mrun = -INFINITY, lrun = 0.f, acc[DPL];
 #pragma unroll
-  for (int r = 0; r < AT_RPW; ++r) {
-    mrun[r] = -INFINITY;
-    lrun[r] = 0.f;
-#pragma unroll
-    for (int e = 0; e < DPL; ++e) acc[r][e] = 0.f;
-  }
+  for (int e = 0; e < DPL; ++e) acc[e] = 0.f;
+  const int qi = q0 + warp;
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int k0 = kt * AT_KT;
-    if (kt + 1 < ntiles) issue_tile(kt + 1);     // buffer (kt+1)&1 was consumed in iteration kt-1 (barrier below)
+    if (kt + AT_NS - 1 < ntiles) issue_tile(kt + AT_NS - 1);   // its ring slot was consumed in iteration kt-1 (barrier below)
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncthreads();
-    const float* Ks = KV + (kt & 1) * 2 * AT_KT * KS;
+    cp_async_wait<AT_NS - 1>();
+    __syncthreads();                             // tile kt landed; QE visible (first iteration)
+    if (kt == 0) timeline_stamp(-12);
+    const float* Ks = KV + (kt % AT_NS) * 2 * AT_KT * KS;
     const float* Vs = Ks + AT_KT * KS;
     const int key = k0 + lane;
     const bool kvalid = key < len;
-    float s[AT_RPW];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains (the 4-cycle FMA latency is the limiter)
 #pragma unroll
-    for (int r = 0; r < AT_RPW; ++r) s[r] = 0.f;
-#pragma unroll 4
     for (int d4 = 0; d4 < DK; d4 += 4) {
       const float4 kd = *reinterpret_cast<const float4*>(Ks + lane * KS + d4);
-#pragma unroll
-      for (int r = 0; r < AT_RPW; ++r) {
-        const float4 qd = *reinterpret_cast<const float4*>(Qs + (warp * AT_RPW + r) * DK + d4);
-        s[r] = fmaf(qd.x, kd.x, s[r]);
-        s[r] = fmaf(qd.y, kd.y, s[r]);
-        s[r] = fmaf(qd.z, kd.z, s[r]);
-        s[r] = fmaf(qd.w, kd.w, s[r]);
-      }
+      const float4 qd = *reinterpret_cast<const float4*>(Qs + warp * KS + d4);
+      s0 = fmaf(qd.x, kd.x, s0); s1 = fmaf(qd.y, kd.y, s1); s2 = fmaf(qd.z, kd.z, s2); s3 = fmaf(qd.w, kd.w, s3);
     }
+    float s = (s0 + s1) + (s2 + s3);
+    const int rel = key - qi + window;
+    if (rel >= 0 && rel < nrel) s += QE[warp * nrel + rel];
+    if (!kvalid) s = -INFINITY;
+    float mx = s;
 #pragma unroll
-    for (int r = 0; r < AT_RPW; ++r) {
-      const int qi = q0 + warp * AT_RPW + r;
-      const int rel = key - qi + window;
-      if (rel >= 0 && rel < nrel) s[r] += QE[(warp * AT_RPW + r) * nrel + rel];
-      if (!kvalid) s[r] = -INFINITY;
-      float mx = s[r];
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float mnew = fmaxf(mrun, mx);
+    const float corr = expf(mrun - mnew);
+    const float p = kvalid ? expf(s - mnew) : 0.f;
+    float ps = p;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float mnew = fmaxf(mrun[r], mx);
-      const float corr = expf(mrun[r] - mnew);
-      const float p = kvalid ? expf(s[r] - mnew) : 0.f;
-      float ps = p;
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    lrun = lrun * corr + ps;
+    mrun = mnew;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-      lrun[r] = lrun[r] * corr + ps;
-      mrun[r] = mnew;
-#pragma unroll
-      for (int e = 0; e < DPL; ++e) acc[r][e] *= corr;
-      Ps[(warp * AT_RPW + r) * AT_KT + lane] = p;
-    }
+    for (int e = 0; e < DPL; ++e) acc[e] *= corr;
+    Ps[warp * AT_KT + lane] = p;
     __syncwarp();
     const int kmax = min(AT_KT, len - k0);
-    for (int kk = 0; kk < kmax; ++kk) {
-      float vv[DPL];
+    if (kmax == AT_KT) {
+      float a2[DPL];
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) vv[e] = Vs[kk * KS + lane + 32 * e];
+      for (int e = 0; e < DPL; ++e) a2[e] = 0.f;
 #pragma unroll
-      for (int r = 0; r < AT_RPW; ++r) {
-        const float p = Ps[(warp * AT_RPW + r) * AT_KT + kk];
+      for (int kk = 0; kk < AT_KT; kk += 2) {            // fully unrolled, two accumulator sets
+        const float p0 = Ps[warp * AT_KT + kk], p1 = Ps[warp * AT_KT + kk + 1];
 #pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, vv[e], acc[r][e]);
+        for (int e = 0; e < DPL; ++e) {
+          acc[e] = fmaf(p0, Vs[kk * KS + lane + 32 * e], acc[e]);
+          a2[e] = fmaf(p1, Vs[(kk + 1) * KS + lane + 32 * e], a2[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[e] += a2[e];
+    } else {
+      for (int kk = 0; kk < kmax; ++kk) {
+        const float pk = Ps[warp * AT_KT + kk];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[e] = fmaf(pk, Vs[kk * KS + lane + 32 * e], acc[e]);
       }
     }
+    for (int m = 0; m < nrel; ++m) {
+      const int kk = qi + m - window - k0;
+      if (kk >= 0 && kk < kmax) {
+        const float pk = Ps[warp * AT_KT + kk];
 #pragma unroll
-    for (int r = 0; r < AT_RPW; ++r) {
-      const int qi = q0 + warp * AT_RPW + r;
-      for (int m = 0; m < nrel; ++m) {
-        const int kk = qi + m - window - k0;
-        if (kk >= 0 && kk < kmax) {
-          const float p = Ps[(warp * AT_RPW + r) * AT_KT + kk];
-#pragma unroll
-          for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(p, Rv[m * DK + lane + 32 * e], acc[r][e]);
-        }
+        for (int e = 0; e < DPL; ++e) acc[e] = fmaf(pk, Rv[m * KS + lane + 32 * e], acc[e]);
       }
     }
     __syncthreads();   // tile buffer (kt&1) and Ps fully consumed before the next prefetch overwrites them
   }
+  timeline_stamp(-13);
+  if (qi < len) {
+    const float inv = 1.f / lrun;
 #pragma unroll
-  for (int r = 0; r < AT_RPW; ++r) {
-    const int qi = q0 + warp * AT_RPW + r;
-    if (qi < len) {
-      const float inv = 1.f / lrun[r];
-#pragma unroll
-      for (int e = 0; e < DPL; ++e) {
-        const float o = acc[r][e] * inv;
-        const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
-        out[idx] = o;
-        if (p_hi) {
-          __nv_bfloat16 hb, lb;
-          split_bf16(o, hb, lb);
-          p_hi[idx] = hb;
-          p_lo[idx] = lb;
-        }
+    for (int e = 0; e < DPL; ++e) {
+      const float o = acc[e] * inv;
+      const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
+      out[idx] = o;
+      if (p_hi) {
+        __nv_bfloat16 hb, lb;
+        split_bf16(o, hb, lb);
+        p_hi[idx] = hb;
+        p_lo[idx] = lb;
       }
     }
   }
@@ -641,7 +722,7 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
 // ------------------------------------------------------------------------------------------------
 constexpr int DDS_TT = 4;      // positions per CTA
 constexpr int DDS_CH = 32;     // 1x1 weight rows (input channels) per cp.async chunk
-constexpr int DDS_NS = 3;      // chunk ring depth
+constexpr int DDS_NS = 4;      // chunk ring depth
 
 struct DdsP {
   const float* x;
@@ -697,6 +778,8 @@ __device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, i
 // 3-deep cp.async ring of 32-row chunks; the first chunks are in flight while the depthwise conv and LN run.
 __global__ void __launch_bounds__(256)
 dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int len = lens[b];
   const int t0 = blockIdx.x * DDS_TT;
@@ -708,20 +791,24 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
   float* ys = Wr + DDS_NS * DDS_CH * C;              // [C][TT]
   float* red = ys + C * DDS_TT;                      // [8][TT]
   const int nch = C / DDS_CH;
-
+  __shared__ uint64_t wfull[DDS_NS];
+  if (c == 0) {
+    for (int i = 0; i < DDS_NS; ++i) mbar_init(&wfull[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // one 32-row chunk of the 1x1 weight matrix = one contiguous bulk copy (ldw == C), issued by a single thread
   auto issue_chunk = [&](int ch) {
-    float* dst = Wr + (ch % DDS_NS) * DDS_CH * C;
-    const float* src = P.pw_w + (long)ch * DDS_CH * P.ldw;
-    for (int i = c; i < DDS_CH * (C / 4); i += blockDim.x) {
-      const int r = i / (C / 4), c4 = (i - r * (C / 4)) * 4;
-      cp_async16(dst + r * C + c4, src + (long)r * P.ldw + c4, 16);
+    if (c == 0) {
+      const int slot = ch % DDS_NS;
+      const uint32_t bytes = (uint32_t)(DDS_CH * C * sizeof(float));
+      mbar_expect_tx(&wfull[slot], bytes);
+      bulk_copy_g2s(Wr + slot * DDS_CH * C, P.pw_w + (long)ch * DDS_CH * P.ldw, bytes, &wfull[slot]);
     }
   };
 #pragma unroll
-  for (int i = 0; i < DDS_NS - 1; ++i) {
+  for (int i = 0; i < DDS_NS - 1; ++i)
     if (i < nch) issue_chunk(i);
-    cp_async_commit();
-  }
 
   float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
   const int half = (P.k - 1) / 2;
@@ -734,7 +821,9 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
     }
     v[i] = a;
   }
+  timeline_stamp(-1);
   block_ln_stats(v, red, C, mean, rstd);
+  timeline_stamp(-2);
   {
     const float g = P.ln1g[c], be = P.ln1b[c];
     float4 o;
@@ -750,10 +839,9 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
     for (int i = 0; i < DDS_TT; ++i) v[i] = bias;
   }
   for (int ch = 0; ch < nch; ++ch) {
-    cp_async_wait<DDS_NS - 2>();
-    __syncthreads();                                 // chunk ch landed (and ys visible); slot (ch-1)%NS is free
+    __syncthreads();                                 // ys visible (first iteration); slot (ch-1)%NS has been consumed
     if (ch + DDS_NS - 1 < nch) issue_chunk(ch + DDS_NS - 1);
-    cp_async_commit();
+    mbar_wait(&wfull[ch % DDS_NS], (ch / DDS_NS) & 1);   // chunk ch landed
     const float* wr = Wr + (ch % DDS_NS) * DDS_CH * C + c;
     const float* yy = ys + ch * DDS_CH * DDS_TT;
 #pragma unroll 8
@@ -763,7 +851,9 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
       v[0] = fmaf(w, y0.x, v[0]); v[1] = fmaf(w, y0.y, v[1]); v[2] = fmaf(w, y0.z, v[2]); v[3] = fmaf(w, y0.w, v[3]);
     }
   }
+  timeline_stamp(-3);
   block_ln_stats(v, red, C, mean, rstd);
+  timeline_stamp(-4);
   {
     const float g = P.ln2g[c], be = P.ln2b[c];
 #pragma unroll
@@ -781,6 +871,8 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
 __global__ void cf_pre_kernel(const float* __restrict__ x0, const float* __restrict__ pre_w, const float* __restrict__ pre_b,
                               const float* __restrict__ cond, float* __restrict__ h, const int* __restrict__ lens,
                               const int* __restrict__ offs, int C) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y, t = blockIdx.x;
   if (t >= lens[b]) return;
   const long row = offs[b] + t;
@@ -815,6 +907,8 @@ __device__ __forceinline__ uint64_t prm_seed(const float* prm) {
 
 __global__ void dp_noise_kernel(const float* __restrict__ eps, int eps_ld, const float* __restrict__ prm, float* __restrict__ za,
                                 float* __restrict__ zb, const int* __restrict__ lens, const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const uint64_t seed = prm_seed(prm);
   const float scale = prm[2];
   const int b = blockIdx.y;
@@ -842,6 +936,8 @@ constexpr int SPL_MAXB = 16;
 
 __global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, float* __restrict__ x1, int nb, float bound,
                                       float sqrt_filter, const int* __restrict__ lens, const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lens[b]) return;
@@ -908,6 +1004,8 @@ __global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, floa
 __global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, const float* __restrict__ prm,
                                 int* __restrict__ wceil, int* __restrict__ cum, int* __restrict__ ylen,
                                 const int* __restrict__ lens, const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.x;
   const int len = lens[b];
   const long base = offs[b];
@@ -949,6 +1047,8 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
 // (never written, zeroed where a TMA-fed kernel reads them) so that a conv halo can never reach a neighbour.
 constexpr int SEQ_GAP = 8;
 __global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restrict__ yoff, int B) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int o = 0;
     for (int b = 0; b < B; ++b) {
@@ -969,6 +1069,8 @@ __global__ void sample_prior_kernel(const float* __restrict__ stats, int I, cons
                                     const int* __restrict__ frm_len, const int* __restrict__ frm_off,
                                     const float* __restrict__ eps, int eps_ld, const float* __restrict__ prm,
                                     float* __restrict__ zp, int* __restrict__ frame_token) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const uint64_t seed = prm_seed(prm);
   const float noise_scale = prm[0];
   const int b = blockIdx.y;
@@ -997,6 +1099,8 @@ __global__ void sample_prior_kernel(const float* __restrict__ stats, int I, cons
 // MRF mean (models.py:1030-1036): out = (a + b + c ...) / n over up to 3 resblock outputs.
 __global__ void mrf_mean_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c, int n,
                                 float* __restrict__ out, long total4) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   float4 s = reinterpret_cast<const float4*>(a)[i];
@@ -1028,6 +1132,8 @@ istft_pqmf_kernel(const float* __restrict__ post, int ldp, const float* __restri
                   int subbands, int nfft, int hop, int taps, int up_total /* frames -> post rows multiplier */,
                   const int* __restrict__ frm_len, const int* __restrict__ frm_off, float* __restrict__ wav, long wav_ld,
                   int packed_out) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int Ty = frm_len[b];
   const int L1 = Ty * up_total + 1;            // post-conv frames
@@ -1103,15 +1209,37 @@ istft_pqmf_kernel(const float* __restrict__ post, int ldp, const float* __restri
   }
 }
 
+// Pulls the weight ranges a call will touch into L2 ahead of their first use (prefetch.global.L2 per 128-byte line).
+// The kernel retires as soon as the prefetches are issued; the fills overlap with the kernels that follow, so the
+// ~130 MB of weights that the benchmark's L2 flush evicts before every step stop costing a DRAM round trip per layer.
+struct PrefRange {
+  const char* p;
+  unsigned long long bytes;
+};
+__global__ void l2_prefetch_kernel(const PrefRange* __restrict__ ranges, int n, int first, int last) {
+  PDL_LAUNCH();
+  for (int r = first + blockIdx.y; r < last && r < n; r += gridDim.y) {
+    const char* base = ranges[r].p;
+    const unsigned long long lines = (ranges[r].bytes + 127ull) >> 7;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < lines;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (i << 7)));
+  }
+}
+
 // int64 -> int32 packing of ids, on device (for the *_dev entry points)
 __global__ void pack_ids_kernel(const int64_t* __restrict__ ids, int t_max, int* __restrict__ out, const int* __restrict__ lens,
                                 const int* __restrict__ offs) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int b = blockIdx.y;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= lens[b]) return;
   out[offs[b] + t] = (int)ids[(long)b * t_max + t];
 }
 __global__ void cast_sid_kernel(const int64_t* __restrict__ sid, int* __restrict__ out, int B) {
+  PDL_LAUNCH();
+  PDL_WAIT();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) out[i] = (int)sid[i];
 }

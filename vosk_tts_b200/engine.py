@@ -42,7 +42,7 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_durations_dev", "vtts_synthesize_dev", "vtts_hop", "vtts_stage_timings",
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
-           "vtts_profile_read_tc"]
+           "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev"]
 
 
 def lib_path():
@@ -75,6 +75,10 @@ def load_library(build_if_missing=True):
     lib.vtts_durations_dev.restype = i32
     lib.vtts_synthesize_dev.argtypes = [vp, vp, i32, vp, C.c_int64]
     lib.vtts_synthesize_dev.restype = i32
+    lib.vtts_infer.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, C.c_uint64, vp, vp, C.c_int64, vp, i32]
+    lib.vtts_infer.restype = i32
+    lib.vtts_infer_dev.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, C.c_uint64, vp, vp, C.c_int64]
+    lib.vtts_infer_dev.restype = i32
     lib.vtts_hop.argtypes = [vp]
     lib.vtts_hop.restype = i32
     lib.vtts_stage_timings.argtypes = [vp, vp, i32]
@@ -96,6 +100,8 @@ def load_library(build_if_missing=True):
     lib.vtts_profile.argtypes = [vp, i32]
     lib.vtts_profile.restype = i32
     lib.vtts_profile_read.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    lib.vtts_timeline.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    lib.vtts_timeline.restype = i32
     lib.vtts_profile_read.restype = i32
     lib.vtts_profile_read_tc.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     lib.vtts_profile_read_tc.restype = i32
@@ -206,13 +212,51 @@ class Engine:
         self._check(self.lib.vtts_synthesize(self.h, _ptr(noise_z), z_ld, _ptr(wav), wav.shape[1], _ptr(idx), max_f))
         return (wav, idx) if want_alignment else wav
 
-    def infer(self, ids, lengths, sid, scales, noise_dp=None, noise_z=None, seed=0):
-        """Both phases.  noise_z may be a callable(max_frames)->[B,C,max_frames] (T_y is data dependent)."""
+    def infer(self, ids, lengths, sid, scales, noise_dp=None, noise_z=None, seed=0, frames_hint=None):
+        """Both phases.  noise_z may be a callable(max_frames)->[B,C,max_frames] (T_y is data dependent).
+        With `frames_hint` (an upper bound on max(y_lengths), e.g. from a previous call) and array/None noise, the
+        fused C entry point vtts_infer is used: one ctypes call, no Python between the two phases."""
+        if frames_hint is not None and not callable(noise_z):
+            ids = np.ascontiguousarray(ids, dtype=np.int64)
+            if ids.ndim == 1:
+                ids = ids[None, :]
+            B, t_max = ids.shape
+            lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(B)
+            sid = np.ascontiguousarray(sid, dtype=np.int64).reshape(B)
+            scales = np.ascontiguousarray(scales, dtype=np.float32).reshape(3)
+            if noise_dp is not None:
+                noise_dp = np.ascontiguousarray(noise_dp, dtype=np.float32).reshape(B, 2, t_max)
+            z_ld = 0
+            if noise_z is not None:
+                noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
+                z_ld = noise_z.shape[2]
+            y_len = np.zeros(B, np.int64)
+            wav = np.zeros((B, int(frames_hint) * self.hop), np.float32)
+            rc = self.lib.vtts_infer(self.h, _ptr(ids), _ptr(lengths), _ptr(sid), B, t_max, _ptr(scales), _ptr(noise_dp),
+                                     _ptr(noise_z), z_ld, int(seed), _ptr(y_len), _ptr(wav), wav.shape[1], None, 0)
+            self._B = B
+            if rc == -4:            # capacity: durations are kept, finish with exact buffers
+                if noise_z is not None and z_ld < int(y_len.max()):
+                    self._check(rc)
+                return self.synthesize(y_len, noise_z), y_len
+            self._check(rc)
+            return wav[:, : int(y_len.max()) * self.hop], y_len
         y_len = self.durations(ids, lengths, sid, scales, noise_dp, seed)
         if callable(noise_z):
             noise_z = noise_z(int(y_len.max()))
         wav = self.synthesize(y_len, noise_z)
         return wav, y_len
+
+    def infer_dev(self, d_ids, lengths, d_sid, B, t_max, scales, d_wav, wav_ld, d_noise_dp=0, d_noise_z=0, z_ld=0, seed=0):
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(B)
+        scales = np.ascontiguousarray(scales, dtype=np.float32).reshape(3)
+        y_len = np.zeros(B, np.int64)
+        self._check(self.lib.vtts_infer_dev(self.h, C.c_void_p(d_ids), _ptr(lengths), C.c_void_p(d_sid), B, t_max, _ptr(scales),
+                                            C.c_void_p(d_noise_dp) if d_noise_dp else None,
+                                            C.c_void_p(d_noise_z) if d_noise_z else None, z_ld, int(seed), _ptr(y_len),
+                                            C.c_void_p(d_wav), wav_ld))
+        self._B = B
+        return y_len
 
     # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr())
     def durations_dev(self, d_ids, lengths, d_sid, B, t_max, scales, d_noise_dp=0, seed=0):
@@ -246,6 +290,16 @@ class Engine:
         if ms < 0:
             raise VttsError(int(ms), self.lib.vtts_last_error(self.h).decode())
         return ms
+
+    def timeline(self, mode):
+        """mode 1: arm, 0: disarm, 2: read -> array [n,2] of (source line, globaltimer ns)."""
+        if mode != 2:
+            self._check(self.lib.vtts_timeline(self.h, int(mode), None, 0, None))
+            return None
+        out = np.zeros((4000, 2), np.uint64)
+        n = C.c_size_t(0)
+        self._check(self.lib.vtts_timeline(self.h, 2, _ptr(out), 4000, C.byref(n)))
+        return out[: n.value].copy()
 
     def set_graphs(self, enable):
         self._check(self.lib.vtts_set_graphs(self.h, int(bool(enable))))

@@ -53,7 +53,12 @@ class VitsSession:
             dp = z = None
             if noise is not None:
                 dp, z = noise.get("dp"), noise.get("z")
-            wav, y_len = self.engine.infer(ids, lengths, sid, scales, dp, z, seed)
+            # one fused C call when the output capacity can be bounded up front (8 frames per phoneme covers the
+            # duration predictor's range in practice; a CAPACITY status falls back to an exact second phase)
+            hint = None if callable(z) else int(8 * ids.shape[1] + 16)
+            if z is not None and not callable(z):
+                hint = min(hint, int(np.asarray(z).shape[2]))
+            wav, y_len = self.engine.infer(ids, lengths, sid, scales, dp, z, seed, frames_hint=hint)
             self.last_y_lengths = y_len
             self.last_wav_lengths = y_len * self.engine.hop
         return [wav[:, None, None, :]]

@@ -222,8 +222,10 @@ def pack(w, cfg, tc=True):
     # ---- text encoder
     P.add("enc.emb", g("enc_p.emb.weight"))
     for i in range(cfg["n_layers"]):
-        enc_layer("enc.%d" % i, "enc_p.encoder", i)
+        enc_layer("enc.%d" % i, "enc_p.encoder", i, with_tc=tc)
     P.conv("enc.proj", g("enc_p.proj.weight"), g("enc_p.proj.bias"))
+    if tc:
+        P.conv_tc("enc.proj", g("enc_p.proj.weight"))
 
     # ---- stochastic duration predictor
     P.conv("dp.pre", g("dp.pre.weight"), g("dp.pre.bias"))
