@@ -33,8 +33,8 @@ def test_golden_single_utterance(engine, name):
     assert np.array_equal(idx[0, : c["Ty"]], c["idx"]), "alignment indices must be bit-exact"
     z_p = engine.debug_read("z_p").reshape(c["Ty"], -1)
     z = engine.debug_read("z").reshape(c["Ty"], -1)
-    assert np.abs(z_p - c["z_p"].T).max() < 1e-4
-    assert np.abs(z - c["z"].T).max() < 1e-4
+    assert np.abs(z_p - c["z_p"].T).max() < 3e-4      # |z_p| ~ 10-16: 2e-5 relative (split-bf16 encoder in mode 2)
+    assert np.abs(z - c["z"].T).max() < 3e-4
     err = np.abs(wav[0, : c["Ty"] * 256] - c["wav"]).max()
     assert err < WAV_TOL
     assert err < WAV_TIGHT, "fp32 path drifted: %g" % err
