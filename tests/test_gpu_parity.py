@@ -164,6 +164,45 @@ def test_graph_replay_equals_eager(engine, cfg):
     assert engine.graph_replays() > n0
 
 
+@pytest.mark.parametrize("env", [{"VTTS_TC_BN": "128"}, {"VTTS_TC_TALL": "1"}, {"VTTS_PDL": "1"}, {"VTTS_CONV_MAXS": "1", "VTTS_CONV_MAXG": "4"}],
+                         ids=["tc-128-wide-tiles", "tc-tall-activation-tiles", "programmatic-dependent-launch", "ffma-no-cluster-4-groups"])
+def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
+    """The tuning switches select different tilings / launch modes of the same kernels (128-wide tcgen05 tiles are what
+    batched calls use automatically); each must still reproduce the reference fixture."""
+    import os
+    from vosk_tts_b200.engine import Engine
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        e = Engine(cfg, packed[0], packed[1], device=0, precision=1)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    for name in ("t128_sid2", "t17_sid2"):
+        g = load_golden(name)
+        c = _case(g, 0)
+        T = len(c["tok"])
+        for rep in range(3):          # eager, capture, replay
+            ylen, dur = e.durations(c["tok"][None], [T], [c["sid"]], g["scales"], c["eps_dp"][None], want_durations=True)
+            assert np.array_equal(dur[0], c["w_ceil"])
+            wav = e.synthesize(ylen, c["eps_z"][None])
+            assert np.abs(wav[0, : c["Ty"] * 256] - c["wav"]).max() < WAV_TIGHT
+    e.close()
+
+
+def test_fused_infer_equals_two_phase_and_handles_capacity(engine, cfg):
+    """vtts_infer (one ABI call) == vtts_durations + vtts_synthesize; a too-small capacity falls back cleanly."""
+    ids, lens, sid = _rand_batch(cfg, 3, 20, 45, 31)
+    ref, yl = engine.infer(ids, lens, sid, (0.8, 1.0, 0.8), seed=11)
+    w1, y1 = engine.infer(ids, lens, sid, (0.8, 1.0, 0.8), seed=11, frames_hint=int(yl.max()) + 7)
+    assert np.array_equal(y1, yl) and np.array_equal(w1[:, : ref.shape[1]], ref)
+    w2, y2 = engine.infer(ids, lens, sid, (0.8, 1.0, 0.8), seed=11, frames_hint=max(1, int(yl.max()) // 2))   # CAPACITY path
+    assert np.array_equal(y2, yl) and np.array_equal(w2, ref)
+
+
 def test_session_run_matches_reference_call_shape(packed, cfg):
     from vosk_tts_b200.session import VitsSession
     s = VitsSession(cfg=cfg, packed=packed, device=0, seed=7, precision=1)

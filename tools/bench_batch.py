@@ -42,11 +42,12 @@ def main():
     for _ in range(3):
         step()
     prof = eng.profile_read(); eng.profile(False)
+    stage = eng.stage_timings()
     n = int(yl.sum()) * eng.hop
     t = sum(ms) / len(ms)
     out = {"workload": "configs[2]: batch %d, 64-256 phonemes, one call" % B, "precision_mode": prec, "ms_per_step": t,
            "samples_per_step": n, "samples_per_s": n / (t / 1e3), "frames": int(yl.sum()), "phonemes": int(lens.sum()),
-           "rtf": (t / 1e3) / (n / 22050.0),
+           "rtf": (t / 1e3) / (n / 22050.0), "stage_ms": stage,
            "conv_tc": {"ms_per_step": prof["tc_ms"] / 3, "tflops_algorithmic": prof["tc_flops"] / (prof["tc_ms"] / 1e3) / 1e12 if prof["tc_ms"] else 0,
                        "launches": prof["tc_launches"] / 3},
            "conv_ffma": {"ms_per_step": prof["conv_ms"] / 3, "tflops": prof["conv_flops"] / (prof["conv_ms"] / 1e3) / 1e12 if prof["conv_ms"] else 0,

@@ -251,55 +251,66 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     const bool rowok = t < L;
     const long orow = out_base + (long)t * P.out_mul + P.out_add;
     const bool gate = (P.epi & TCE_GATE) != 0;
-    const int ocb = gate ? (co0 >> 1) : co0;               // first output channel of this CTA
-    const int nvalid = gate ? min(BN / 2, (P.Cout >> 1) - ocb) : min(BN, P.Cout - co0);   // valid output channels
-    float rr[BN];
-    if (P.res && rowok) {
-      const float* rp = P.res + orow * (long)P.ldr + P.roff + ocb;
+    const bool relu = (P.epi & TCE_RELU) != 0;
+    constexpr int EN = 64;                                 // columns handled per epilogue pass
+    float rr[EN];
+    auto load_res = [&](int eh) {                          // residual of pass `eh` (64 accumulator columns) into registers
+      const int co0e = co0 + eh * EN;
+      const int ocb = gate ? (co0e >> 1) : co0e;
+      const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - co0e);
+      if (P.res && rowok && nvalid > 0) {
+        const float* rp = P.res + orow * (long)P.ldr + P.roff + ocb;
 #pragma unroll
-      for (int i = 0; i < BN; i += 4) {
-        if (i + 4 <= nvalid) {
-          const float4 q4 = *reinterpret_cast<const float4*>(rp + i);
-          rr[i] = q4.x; rr[i + 1] = q4.y; rr[i + 2] = q4.z; rr[i + 3] = q4.w;
-        } else {
+        for (int i = 0; i < EN; i += 4) {
+          if (i + 4 <= nvalid) {
+            const float4 q4 = *reinterpret_cast<const float4*>(rp + i);
+            rr[i] = q4.x; rr[i + 1] = q4.y; rr[i + 2] = q4.z; rr[i + 3] = q4.w;
+          } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) rr[i + e] = (i + e < nvalid) ? rp[i + e] : 0.f;
+            for (int e = 0; e < 4; ++e) rr[i + e] = (i + e < nvalid) ? rp[i + e] : 0.f;
+          }
         }
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int i = 0; i < BN; ++i) rr[i] = 0.f;
-    }
+        for (int i = 0; i < EN; ++i) rr[i] = 0.f;
+      }
+    };
+    load_res(0);
     asm volatile("bar.sync 1, 128;" ::: "memory");          // bias_s visible to the 4 epilogue warps
     mbar_wait(tmem_full, 0);
     if (threadIdx.x == 64) TC_STAMP(6);
     tc_fence_after();
-    float v[BN];
-    {
-      uint32_t rg[BN];
+#pragma unroll 1
+    for (int eh = 0; eh < BN / EN; ++eh) {
+      const int co0e = co0 + eh * EN;
+      if (co0e >= P.Cout) break;
+      if (eh > 0) load_res(eh);
+      const int ocb = gate ? (co0e >> 1) : co0e;           // first output channel of this pass
+      const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - co0e);
+      float v[EN];
+      {
+        uint32_t rg[EN];
 #pragma unroll
-      for (int n0 = 0; n0 < BN; n0 += 16) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)n0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
-              "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
-              "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
-            : "r"(taddr));
+        for (int n0 = 0; n0 < EN; n0 += 16) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(eh * EN + n0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
+                "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
+                "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
+              : "r"(taddr));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < EN; ++i) v[i] = __uint_as_float(rg[i]) + bias_s[eh * EN + i];
       }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < BN; ++i) v[i] = __uint_as_float(rg[i]) + bias_s[i];
-    }
-    if (rowok) {
-      constexpr int NO = BN;                                // outputs per row without gate; BN/2 with gate
+      if (!rowok) continue;
       if (gate) {
 #pragma unroll
-        for (int i = 0; i < BN / 2; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
+        for (int i = 0; i < EN / 2; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
       }
-      const bool relu = (P.epi & TCE_RELU) != 0;
 #pragma unroll
-      for (int i = 0; i < NO; ++i) {
+      for (int i = 0; i < EN; ++i) {
         float u = v[i];
         if (relu) u = fmaxf(u, 0.f);
         v[i] = u * P.alpha + rr[i];
@@ -308,7 +319,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         float* yr = P.y + orow * (long)P.ldy + P.yoff + ocb;
         const bool al = ((P.ldy | P.yoff) & 3) == 0;
 #pragma unroll
-        for (int i = 0; i < NO; i += 4) {
+        for (int i = 0; i < EN; i += 4) {
           if (al && i + 4 <= nvalid) {
             *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
           } else {
@@ -323,7 +334,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + ocb;
         const bool al = ((P.ldp | P.poff) & 7) == 0;
 #pragma unroll
-        for (int i = 0; i < NO; i += 8) {
+        for (int i = 0; i < EN; i += 8) {
           __align__(16) __nv_bfloat16 hb[8], lb[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {

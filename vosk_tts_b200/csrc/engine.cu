@@ -184,12 +184,17 @@ struct vtts_engine {
   int debug_flags = 0;
   Buf<char> h_pin, h_pin_in, h_pin_len, h_pin_z;  // pinned staging (host): outputs, phase-1 inputs, lengths, noise_z
   Buf<float> d_prm;                              // per-call scalars (see kernels.cuh prm_seed)
+  int* h_map = nullptr;                          // mapped pinned host memory: [0] sequence flag, lengths, offsets
+  int* d_map = nullptr;                          // its device alias
+  size_t map_cap = 0;
+  int call_seq = 0;
+  bool use_poll = true;
   // CUDA graphs: a call shape seen before is captured once and replayed (launch-bound at batch 1)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = false;   // PDL measured slower inside graphs
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -574,7 +579,20 @@ CUtensorMap vtts_engine::make_map(const void* base, int C, long rows, int box_ro
 
 // Grouped tensor-core conv launch (conv_tc.cuh).  One CTA = 128 rows x 64 output channels of one problem.
 void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB) {
-  constexpr int BN = 64;
+  // 128-wide channel tiles halve the activation traffic and run the MMA at its smem-operand optimum, but halve the CTA
+  // count: used once the launch still fills the machine (batched calls), or when forced (VTTS_TC_BN).
+  int BN = 64;
+  {
+    const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+    long ctas128 = 0;
+    bool wide = true;
+    for (const TcSpec& q : ps) {
+      if (q.Cout < 128) wide = false;
+      for (int b = 0; b < nB; ++b) ctas128 += (long)((hl[b] * rmul + q.in_extra + TC_BM - 1) / TC_BM) * ((q.Cout + 127) / 128);
+    }
+    if (wide && ctas128 >= 2 * 148) BN = 128;
+    if (tc_bn == 64 || tc_bn == 128) BN = tc_bn;
+  }
   REQUIRE(!ps.empty() && (int)ps.size() <= TC_MAXP, VTTS_ERR_INVALID, "bad grouped tensor-core conv");
   static TcBatch tbs;   // 2.6 KB: keep it off the stack frame of every caller
   TcBatch& tb = tbs;
@@ -586,6 +604,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     if (nr > 192) tall = false;              // shared-memory budget of the activation ring (and TMA box <= 256)
     maxNR = std::max(maxNR, nr);
   }
+  if (BN == 128) tall = false;             // the 128-wide weight ring leaves no room for tall activation tiles
   if (!tall) maxNR = TC_BM;
   tb.tall = tall ? 1 : 0;
   tb.baseoff = tc_baseoff;
@@ -627,7 +646,8 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     ++tc_prof_launches;
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
   }
-  klaunch(conv_tc_kernel<BN>, dim3(grid), dim3(TC_THREADS), (size_t)(tc_smem_bytes<BN>(tb.a_bytes)), tb, lens, offs);
+  if (BN == 128) klaunch(conv_tc_kernel<128>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes<128>(tb.a_bytes), tb, lens, offs);
+  else klaunch(conv_tc_kernel<64>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes<64>(tb.a_bytes), tb, lens, offs);
   CK(cudaGetLastError());
   if (profiling) {
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used + 1], stream));
@@ -1147,11 +1167,11 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   int* fo = ensure(d_frm_off, B + 1);
   klaunch(duration_kernel, dim3(B), dim3(256), (size_t)(0), zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to);
   CK(cudaGetLastError());
-  klaunch(frame_offsets_kernel, dim3(1), dim3(32), (size_t)(0), fl, fo, B);
+  klaunch(frame_offsets_kernel, dim3(1), dim3(32), (size_t)(0), fl, fo, B, (volatile int*)(use_poll ? d_map : nullptr), (const float*)prm);
   CK(cudaGetLastError());
   launches += 2;
   if (!capturing) CK(cudaEventRecord(ev[3], stream));
-  {
+  if (!use_poll) {
     int* p_len = reinterpret_cast<int*>(ensure_pinned(h_pin_len, (size_t)(2 * B + 2) * sizeof(int)));
     CK(cudaMemcpyAsync(p_len, fl, B * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(p_len + B, fo, (B + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -1186,11 +1206,47 @@ void vtts_engine::stage1(const int* ids_packed_host, const int* sid_host, int t_
   const uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
   memcpy(&pp.prm[4], &lo, 4);
   memcpy(&pp.prm[5], &hi, 4);
-  pp.prm[6] = pp.prm[7] = 0.f;
+  if (use_poll) {
+    const size_t need = (size_t)(2 * B + 4);
+    if (need > map_cap) {
+      REQUIRE(!capturing, VTTS_ERR_STATE, "mapped buffer growth during capture");
+      if (h_map) { CK(cudaStreamSynchronize(stream)); CK(cudaFreeHost(h_map)); h_map = nullptr; }
+      map_cap = need + 256;
+      CK(cudaHostAlloc(reinterpret_cast<void**>(&h_map), map_cap * sizeof(int), cudaHostAllocMapped));
+      CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_map), h_map, 0));
+      h_map[0] = 0;
+      ++ws_gen;
+    }
+    call_seq = (call_seq % 1000000) + 1;
+    memcpy(&pp.prm[6], &call_seq, 4);
+  } else {
+    pp.prm[6] = 0.f;
+  }
+  pp.prm[7] = 0.f;
   if (noise_dp_host) memcpy(pp.eps, noise_dp_host, (size_t)B * 2 * t_max * sizeof(float));
 }
 
 void vtts_engine::finish1() {
+  if (use_poll) {
+    // spin on the flag the last phase-1 kernel writes into mapped host memory (bounded; then fall back to a sync)
+    volatile int* flag = h_map;
+    bool seen = false;
+    for (long spin = 0; spin < 40000000L; ++spin) {
+      if (*flag == call_seq) { seen = true; break; }
+      if ((spin & 0xFFFFF) == 0xFFFFF && cudaStreamQuery(stream) != cudaErrorNotReady) break;   // finished or failed
+    }
+    if (!seen) {
+      CK(cudaStreamSynchronize(stream));
+      REQUIRE(*flag == call_seq, VTTS_ERR_CUDA, "phase 1 finished without publishing the utterance lengths");
+    }
+    h_frm_len.assign(h_map + 1, h_map + 1 + B);
+    h_frm_off.assign(h_map + 1 + B, h_map + 1 + 2 * B + 1);
+    Tfrm = h_frm_off[B];
+    maxFrm = 0;
+    for (int b = 0; b < B; ++b) maxFrm = std::max(maxFrm, h_frm_len[b]);
+    have_durations = true;
+    return;
+  }
   CK(cudaStreamSynchronize(stream));
   const int* p_len = reinterpret_cast<const int*>(h_pin_len.p);
   h_frm_len.assign(p_len, p_len + B);
@@ -1599,6 +1655,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
       CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>(24 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -1617,7 +1674,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_MAXG")) h->conv_max_g = std::max(1, std::min(4, atoi(e)));
     if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
+    if (const char* e = getenv("VTTS_TC_BN")) h->tc_bn = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
+    if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
@@ -1653,6 +1712,7 @@ void vtts_destroy(vtts_handle h) {
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   fr(h->d_prm.p);
   fr(h->d_pref.p);
+  if (h->h_map) cudaFreeHost(h->h_map);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->tc_prof_ev) if (e) cudaEventDestroy(e);

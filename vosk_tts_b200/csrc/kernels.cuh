@@ -1046,16 +1046,26 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
 // Packed row offsets of the utterances at frame resolution.  SEQ_GAP empty rows separate consecutive utterances
 // (never written, zeroed where a TMA-fed kernel reads them) so that a conv halo can never reach a neighbour.
 constexpr int SEQ_GAP = 8;
-__global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restrict__ yoff, int B) {
+// `host_out` (optional) is pinned host memory mapped into the device address space: the lengths and offsets are
+// published there, followed by the call's sequence number (prm[6]), so the host can pick them up by polling instead
+// of paying for copy nodes plus a stream synchronisation between the two phases of a call.
+__global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restrict__ yoff, int B, volatile int* host_out,
+                                     const float* __restrict__ prm) {
   PDL_LAUNCH();
   PDL_WAIT();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     int o = 0;
     for (int b = 0; b < B; ++b) {
       yoff[b] = o;
+      if (host_out) { host_out[1 + b] = ylen[b]; host_out[1 + B + b] = o; }
       o += ylen[b] + (b + 1 < B ? SEQ_GAP : 0);
     }
     yoff[B] = o;
+    if (host_out) {
+      host_out[1 + 2 * B] = o;
+      __threadfence_system();
+      host_out[0] = __float_as_int(prm[6]);
+    }
   }
 }
 
