@@ -1134,7 +1134,7 @@ __global__ void mrf_mean_kernel(const float* __restrict__ a, const float* __rest
 // (= TL_M*subbands output samples) of one utterance.
 //   post rows: per utterance L1 = 16*Ty + 1 frames of `subbands*(n_fft+2)` channels.
 // ------------------------------------------------------------------------------------------------
-constexpr int TL_M = 256;       // subband samples per CTA
+constexpr int TL_M = 64;        // subband samples per CTA (256 output samples): 4x more CTAs than the first version, 40 -> ~12 us at batch 1
 constexpr int TL_THREADS = 256;
 
 __global__ void __launch_bounds__(TL_THREADS)
