@@ -114,6 +114,15 @@ int vtts_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_h
                    const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
                    int64_t* y_lengths_host, float* d_wav, int64_t wav_ld);
 
+/* Streaming synthesis of one long utterance (BASELINE.json configs[4]): after vtts_durations, vtts_flow runs the
+ * alignment, sampling and the flow once; vtts_decode_chunk then vocodes latent frames [f0, f1) with a
+ * vtts_decoder_halo()-frame halo on each side that is computed and discarded ("overlap-discard": exact, because the
+ * halo covers the decoder's receptive field), so audio can be handed out chunk by chunk.  B must be 1.
+ * wav receives hop*(f1-f0) samples. */
+int vtts_decoder_halo(vtts_handle h);
+int vtts_flow(vtts_handle h, const float* noise_z, int z_ld);
+int vtts_decode_chunk(vtts_handle h, int f0, int f1, float* wav, int64_t wav_capacity);
+
 /* Samples produced per latent frame (256 for the reference config). */
 int vtts_hop(vtts_handle h);
 /* CUDA-event time (ms) of each stage of the last call: [0] encoder, [1] duration predictor +

@@ -136,6 +136,19 @@ def test_long_utterance_2000_phonemes(engine, folded, cfg):
     assert wav.shape[1] == int(ylen[0]) * 256 and np.isfinite(wav).all()
 
 
+def test_chunked_vocoder_equals_monolithic(engine, cfg):
+    """BASELINE.json configs[4] mechanism: flow once, vocode 64-frame chunks with a 24-frame halo that is discarded;
+    the concatenation equals the monolithic waveform (the halo covers the decoder's receptive field)."""
+    rng = np.random.RandomState(4)
+    ids = rng.randint(0, cfg["n_vocab"], size=(1, 300)).astype(np.int64)
+    mono, yl = engine.infer(ids, [300], [2], (0.8, 1.0, 0.8), seed=9)
+    chunks = list(engine.synthesize_stream(ids, 2, (0.8, 1.0, 0.8), chunk_frames=64, seed=9))
+    wav = np.concatenate(chunks)
+    assert len(chunks) == -(-int(yl[0]) // 64) and wav.size == mono.shape[1]
+    tol = 2e-6 if engine.precision == 0 else 5e-5
+    assert np.abs(wav - mono[0]).max() < tol
+
+
 def test_error_paths(engine, cfg):
     from vosk_tts_b200.engine import VttsError
     ids, lens, sid = _rand_batch(cfg, 2, 8, 16, 2)

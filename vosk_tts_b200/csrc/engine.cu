@@ -381,7 +381,10 @@ struct vtts_engine {
   void finish1();
   void phase1(const int* ids_packed_host, const int64_t* d_ids64, int t_max, const int64_t* d_sid64, const int* sid_host,
               const float* noise_dp, bool noise_on_device);
-  void phase2(const float* noise_z, int z_ld, bool noise_on_device);
+  void phase2(const float* noise_z, int z_ld, bool noise_on_device, bool run_decoder = true);
+  void decode(float* z, const int* fl, const int* fo);
+  bool have_latent = false;
+  Buf<int> d_chunk;                              // [len, off, off_end] of the chunk being decoded
 };
 
 namespace {
@@ -1260,7 +1263,7 @@ void vtts_engine::finish1() {
 // ---------------------------------------------------------------------------------------------------
 // Phase 2: alignment + prior sampling, flow^-1, decoder.
 // ---------------------------------------------------------------------------------------------------
-void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
+void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, bool run_decoder) {
   const vtts_config& c = cfg;
   const int H = c.hidden_channels, I = c.inter_channels, half = I / 2;
   const size_t F = (size_t)Tfrm;
@@ -1376,6 +1379,16 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device) {
   }
   if (!capturing) CK(cudaEventRecord(ev[5], stream));
 
+  if (!run_decoder) return;
+  decode(z, fl, fo);
+}
+
+// Decoder over the utterance rows described by (fl, fo) -- the whole batch, or one halo-extended chunk of a single
+// utterance (vtts_decode_chunk).
+void vtts_engine::decode(float* z, const int* fl, const int* fo) {
+  const vtts_config& c = cfg;
+  const int I = c.inter_channels;
+  const size_t F = (size_t)Tfrm;
   // ---- decoder (models.py:1016-1054 / 872-891)
   if (tc) {
     decoder_tc(z, fl, fo);
@@ -1533,6 +1546,7 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
   h->Ttok = off;
   h->maxTok = mx;
   h->have_durations = false;
+  h->have_latent = false;
 }
 
 }  // namespace
@@ -1743,6 +1757,63 @@ int vtts_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengt
 int vtts_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
   if (!d_wav) return VTTS_ERR_INVALID;
   return guarded(h, [&] { impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld); });
+}
+
+// ---- streaming: flow once, then decode halo-extended chunks (the decoder's receptive field is
+// +-23.9 latent frames, so a chunk decoded with a 24-frame halo on each side reproduces the monolithic output).
+int vtts_decoder_halo(vtts_handle h) { return h ? 24 : 0; }
+
+int vtts_flow(vtts_handle h, const float* noise_z, int z_ld) {
+  return guarded(h, [&] {
+    REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_flow called without vtts_durations");
+    REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+    if (noise_z) {
+      const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
+      char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));
+      memcpy(pin, noise_z, n * sizeof(float));
+    }
+    h->last_graphed = false;
+    h->phase2(noise_z, z_ld, false, /*run_decoder=*/false);
+    CK(cudaStreamSynchronize(h->stream));
+    h->have_durations = false;
+    h->have_latent = true;
+  });
+}
+
+int vtts_decode_chunk(vtts_handle h, int f0, int f1, float* wav, int64_t wav_capacity) {
+  if (!wav) return VTTS_ERR_INVALID;
+  return guarded(h, [&] {
+    REQUIRE(h->have_latent, VTTS_ERR_STATE, "vtts_decode_chunk called without vtts_flow");
+    REQUIRE(h->B == 1, VTTS_ERR_INVALID, "chunked decoding handles one utterance per call");
+    const int T = h->h_frm_len[0];
+    REQUIRE(0 <= f0 && f0 < f1 && f1 <= T, VTTS_ERR_INVALID, "chunk out of range");
+    REQUIRE((int64_t)(f1 - f0) * h->hop <= wav_capacity, VTTS_ERR_CAPACITY, "chunk does not fit the output buffer");
+    const int halo = 24;
+    const int lo = std::max(0, f0 - halo), hi = std::min(T, f1 + halo);
+    int* dc = h->ensure(h->d_chunk, 4);
+    int* pin = reinterpret_cast<int*>(h->ensure_pinned(h->h_pin_len, 64));
+    pin[0] = hi - lo; pin[1] = lo; pin[2] = hi;
+    CK(cudaMemcpyAsync(dc, pin, 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    // the launch helpers size grids and split-K from the host copies of the lengths: point them at the chunk
+    const std::vector<int> len0 = h->h_frm_len, off0 = h->h_frm_off;
+    const int max0 = h->maxFrm;
+    h->h_frm_len.assign(1, hi - lo);
+    h->h_frm_off = {lo, hi};
+    h->maxFrm = hi - lo;
+    try {
+      h->last_graphed = false;
+      h->decode(h->d_z.p, dc, dc + 1);
+    } catch (...) {
+      h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0;
+      throw;
+    }
+    h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0;
+    const size_t n = (size_t)(f1 - f0) * h->hop;
+    float* pw = reinterpret_cast<float*>(h->ensure_pinned(n * sizeof(float)));
+    CK(cudaMemcpyAsync(pw, h->d_wav.p + (size_t)f0 * h->hop, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    memcpy(wav, pw, n * sizeof(float));
+  });
 }
 
 int vtts_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max, const float* scales,

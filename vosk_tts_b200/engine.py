@@ -42,7 +42,8 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_durations_dev", "vtts_synthesize_dev", "vtts_hop", "vtts_stage_timings",
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
-           "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev"]
+           "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev",
+           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk"]
 
 
 def lib_path():
@@ -79,6 +80,12 @@ def load_library(build_if_missing=True):
     lib.vtts_infer.restype = i32
     lib.vtts_infer_dev.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, i32, C.c_uint64, vp, vp, C.c_int64]
     lib.vtts_infer_dev.restype = i32
+    lib.vtts_decoder_halo.argtypes = [vp]
+    lib.vtts_decoder_halo.restype = i32
+    lib.vtts_flow.argtypes = [vp, vp, i32]
+    lib.vtts_flow.restype = i32
+    lib.vtts_decode_chunk.argtypes = [vp, i32, i32, vp, C.c_int64]
+    lib.vtts_decode_chunk.restype = i32
     lib.vtts_hop.argtypes = [vp]
     lib.vtts_hop.restype = i32
     lib.vtts_stage_timings.argtypes = [vp, vp, i32]
@@ -257,6 +264,23 @@ class Engine:
                                             C.c_void_p(d_wav), wav_ld))
         self._B = B
         return y_len
+
+    # ---- streaming (one utterance): flow once, then vocode chunk by chunk
+    def synthesize_stream(self, ids, sid, scales, chunk_frames=64, noise_dp=None, noise_z=None, seed=0):
+        """Generator of float32 chunks; concatenated they equal `infer(...)` of the same inputs."""
+        ids = np.ascontiguousarray(ids, dtype=np.int64).reshape(1, -1)
+        y_len = self.durations(ids, [ids.shape[1]], [sid], scales, noise_dp, seed)
+        T = int(y_len[0])
+        z_ld = 0
+        if noise_z is not None:
+            noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
+            z_ld = noise_z.shape[2]
+        self._check(self.lib.vtts_flow(self.h, _ptr(noise_z), z_ld))
+        for f0 in range(0, T, chunk_frames):
+            f1 = min(T, f0 + chunk_frames)
+            out = np.zeros((f1 - f0) * self.hop, np.float32)
+            self._check(self.lib.vtts_decode_chunk(self.h, f0, f1, _ptr(out), out.size))
+            yield out
 
     # ---- device-buffer path (raw pointers, e.g. torch tensors' data_ptr())
     def durations_dev(self, d_ids, lengths, d_sid, B, t_max, scales, d_noise_dp=0, seed=0):
