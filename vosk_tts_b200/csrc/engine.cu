@@ -194,7 +194,7 @@ struct vtts_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = false;   // PDL measured slower inside graphs
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -661,16 +661,23 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
 
 void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl) {
   const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
-  dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, B);
-  const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
   __nv_bfloat16* ph = pl ? pl->hi : nullptr;
   __nv_bfloat16* plo = pl ? pl->lo : nullptr;
-  switch (dk / 32) {
-    case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
-    default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo); break;
+  // register-blocked variant (4 query rows per warp) once the launch is throughput bound
+  const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+  long rows = 0;
+  for (int b = 0; b < B; ++b) rows += hl[b];
+  const int R = (attn_rows == 1 || attn_rows == 4) ? attn_rows : (rows * cfg.n_heads >= 8L * 2 * 148 * 4 ? 4 : 1);
+  const int QT = 8 * R;
+  dim3 grid((maxLen + QT - 1) / QT, cfg.n_heads, B);
+  const size_t smem = (size_t)attn_smem_floats(dk, nrel, R) * sizeof(float);
+#define ATTN_CASE(D, RR) klaunch(attn_kernel<D, RR>, grid, dim3(AT_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo)
+  if (R == 4) {
+    switch (dk / 32) { case 1: ATTN_CASE(1, 4); break; case 2: ATTN_CASE(2, 4); break; case 3: ATTN_CASE(3, 4); break; default: ATTN_CASE(4, 4); break; }
+  } else {
+    switch (dk / 32) { case 1: ATTN_CASE(1, 1); break; case 2: ATTN_CASE(2, 1); break; case 3: ATTN_CASE(3, 1); break; default: ATTN_CASE(4, 1); break; }
   }
+#undef ATTN_CASE
   CK(cudaGetLastError());
   ++launches;
 }
@@ -956,19 +963,7 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
                                 const float* cadd_after) {
   const int nB = B;
   launch_conv({mk(L.qkv, x, Hc, 0, qkv, 3 * Hc, 0, 1, 0)}, 1, lens, offs, maxLen, nB);
-  {
-    const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
-    dim3 grid((maxLen + AT_QT - 1) / AT_QT, cfg.n_heads, nB);
-    const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
-    switch (dk / 32) {
-      case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-      case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-      case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-      default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-    }
-    CK(cudaGetLastError());
-    ++launches;
-  }
+  launch_attn(qkv, ao, L, Hc, lens, offs, maxLen, nullptr);
   launch_conv({mk(L.o, ao, Hc, 0, y, Hc, 0, 1, 0)}, 1, lens, offs, maxLen, nB);
   dim3 lg((maxLen + 3) / 4, nB);
   klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), x, y, L.ln1.g, L.ln1.b, nullptr, nullptr, 0, xb, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
@@ -1320,19 +1315,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
       // encoder_layer writes its result into `xa` (== h) -- we need h preserved for the residual, so run the
       // layer on explicit buffers instead of the ping-pong helper:
       launch_conv({mk(W.tr.qkv, h, H, 0, fqkv, 3 * H, 0, 1, 0)}, 1, fl, fo, maxFrm, B);
-      {
-        const int dk = H / c.n_heads, nrel = 2 * c.window_size + 1;
-        dim3 grid((maxFrm + AT_QT - 1) / AT_QT, c.n_heads, B);
-        const size_t smem = (size_t)(2 * AT_NS * AT_KT * (dk + 4) + AT_QT * (dk + 4) + 2 * nrel * (dk + 4) + AT_QT * nrel + AT_QT * AT_KT) * sizeof(float);
-        switch (dk / 32) {
-          case 1: klaunch(attn_kernel<1>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-          case 2: klaunch(attn_kernel<2>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-          case 3: klaunch(attn_kernel<3>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-          default: klaunch(attn_kernel<4>, dim3(grid), dim3(AT_THREADS), (size_t)(smem), fqkv, 3 * H, fao, H, W.tr.relk, W.tr.relv, c.n_heads, c.window_size, fl, fo, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr); break;
-        }
-        CK(cudaGetLastError());
-        ++launches;
-      }
+      launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, nullptr);
       launch_conv({mk(W.tr.o, fao, H, 0, fy, H, 0, 1, 0)}, 1, fl, fo, maxFrm, B);
       dim3 lg((maxFrm + 3) / 4, B);
       klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xa, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, xb2, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
@@ -1689,6 +1672,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
     if (const char* e = getenv("VTTS_TC_BN")) h->tc_bn = atoi(e);
+    if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
@@ -1696,10 +1680,14 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->bind_weights();
     h->build_prefetch_list();
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CK(cudaFuncSetAttribute(attn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(attn_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
     CK(cudaFuncSetAttribute(conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));

@@ -538,15 +538,16 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
 // with -1e4 before the softmax (:183), whose exp underflows to exactly 0 in fp32.
 // Online softmax over key tiles of 32; 4 warps x 4 query rows per CTA.
 // ------------------------------------------------------------------------------------------------
-constexpr int AT_QT = 8, AT_KT = 32, AT_THREADS = 256;   // 8 warps, one query row each
+constexpr int AT_KT = 32, AT_THREADS = 256;              // 8 warps; R query rows per warp -> 8*R rows per CTA
 constexpr int AT_NS = 4;                                   // K/V tile ring depth (tiles are latency-, not bandwidth-bound)
 
-template <int DPL>
-constexpr int attn_smem_floats(int nrel) {
-  return 2 * AT_NS * AT_KT * (32 * DPL + 4) + AT_QT * (32 * DPL + 4) + 2 * nrel * (32 * DPL + 4) + AT_QT * nrel + AT_QT * AT_KT;
+constexpr int attn_smem_floats(int dk, int nrel, int R) {
+  return 2 * AT_NS * AT_KT * (dk + 4) + 8 * R * (dk + 4) + 2 * nrel * (dk + 4) + 8 * R * nrel + 8 * R * AT_KT;
 }
 
-template <int DPL>  // dk = 32*DPL
+// R = 1: lowest latency (batch 1, short utterances).  R = 4: every K/V shared-memory read is reused by four query
+// rows (register blocking) -- 2.5x fewer LDS per FLOP, for batched / long utterances where attention is throughput bound.
+template <int DPL, int R>  // dk = 32*DPL
 __global__ void __launch_bounds__(AT_THREADS)
 attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
             const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
@@ -555,9 +556,10 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   PDL_WAIT();
   constexpr int DK = 32 * DPL;
   constexpr int KS = DK + 4;              // row pitch: 16B aligned (cp.async / LDS.128), conflict-free for both access patterns
+  constexpr int QT = 8 * R;
   const int b = blockIdx.z, head = blockIdx.y;
   const int len = lens[b];
-  const int q0 = blockIdx.x * AT_QT;
+  const int q0 = blockIdx.x * QT;
   if (q0 >= len) return;
   const long base = offs[b];
   const int HT = n_heads * DK;
@@ -566,10 +568,10 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   extern __shared__ __align__(16) float sm[];
   float* KV = sm;                                  // [NS stages][K | V][KT][KS]
   float* Qs = KV + 2 * AT_NS * AT_KT * KS;         // [QT][KS]
-  float* Rk = Qs + AT_QT * KS;                     // [nrel][KS]
+  float* Rk = Qs + QT * KS;                        // [nrel][KS]
   float* Rv = Rk + nrel * KS;                      // [nrel][KS]
   float* QE = Rv + nrel * KS;                      // [QT][nrel]
-  float* Ps = QE + AT_QT * nrel;                   // [QT][KT]
+  float* Ps = QE + QT * nrel;                      // [QT][KT]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (len + AT_KT - 1) / AT_KT;
@@ -594,7 +596,7 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   }
 
   // Q rows (pre-scaled by 1/sqrt(dk) as attentions.py:171 does) and both relative-position tables into shared memory
-  for (int i = tid; i < AT_QT * (DK / 4); i += AT_THREADS) {
+  for (int i = tid; i < QT * (DK / 4); i += AT_THREADS) {
     const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
     const int t = q0 + r;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -610,7 +612,7 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   }
   __syncthreads();
   // q . Ek for the 2W+1 relative offsets: one thread per (row, offset)
-  for (int i = tid; i < AT_QT * nrel; i += AT_THREADS) {
+  for (int i = tid; i < QT * nrel; i += AT_THREADS) {
     const int r = i / nrel, m = i - r * nrel;
     float a = 0.f;
 #pragma unroll 4
@@ -623,10 +625,15 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
   }
   timeline_stamp(-11);
 
-  float mrun = -INFINITY, lrun = 0.f, acc[DPL];
+  float mrun[R], lrun[R], acc[R][DPL];
 #pragma unroll
-  for (int e = 0; e < DPL; ++e) acc[e] = 0.f;
-  const int qi = q0 + warp;
+  for (int r = 0; r < R; ++r) {
+    mrun[r] = -INFINITY;
+    lrun[r] = 0.f;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[r][e] = 0.f;
+  }
+  const int row0 = warp * R;                       // first local query row of this warp
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int k0 = kt * AT_KT;
@@ -639,78 +646,109 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
     const float* Vs = Ks + AT_KT * KS;
     const int key = k0 + lane;
     const bool kvalid = key < len;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;      // four independent chains (the 4-cycle FMA latency is the limiter)
+    float s0[R], s1[R], s2[R], s3[R];              // four independent chains per row (the 4-cycle FMA latency is the limiter)
+#pragma unroll
+    for (int r = 0; r < R; ++r) s0[r] = s1[r] = s2[r] = s3[r] = 0.f;
 #pragma unroll
     for (int d4 = 0; d4 < DK; d4 += 4) {
       const float4 kd = *reinterpret_cast<const float4*>(Ks + lane * KS + d4);
-      const float4 qd = *reinterpret_cast<const float4*>(Qs + warp * KS + d4);
-      s0 = fmaf(qd.x, kd.x, s0); s1 = fmaf(qd.y, kd.y, s1); s2 = fmaf(qd.z, kd.z, s2); s3 = fmaf(qd.w, kd.w, s3);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 qd = *reinterpret_cast<const float4*>(Qs + (row0 + r) * KS + d4);
+        s0[r] = fmaf(qd.x, kd.x, s0[r]); s1[r] = fmaf(qd.y, kd.y, s1[r]);
+        s2[r] = fmaf(qd.z, kd.z, s2[r]); s3[r] = fmaf(qd.w, kd.w, s3[r]);
+      }
     }
-    float s = (s0 + s1) + (s2 + s3);
-    const int rel = key - qi + window;
-    if (rel >= 0 && rel < nrel) s += QE[warp * nrel + rel];
-    if (!kvalid) s = -INFINITY;
-    float mx = s;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float mnew = fmaxf(mrun, mx);
-    const float corr = expf(mrun - mnew);
-    const float p = kvalid ? expf(s - mnew) : 0.f;
-    float ps = p;
+    for (int r = 0; r < R; ++r) {
+      const int qi = q0 + row0 + r;
+      float s = (s0[r] + s1[r]) + (s2[r] + s3[r]);
+      const int rel = key - qi + window;
+      if (rel >= 0 && rel < nrel) s += QE[(row0 + r) * nrel + rel];
+      if (!kvalid) s = -INFINITY;
+      float mx = s;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
-    lrun = lrun * corr + ps;
-    mrun = mnew;
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float mnew = fmaxf(mrun[r], mx);
+      const float corr = expf(mrun[r] - mnew);
+      const float p = kvalid ? expf(s - mnew) : 0.f;
+      float ps = p;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) acc[e] *= corr;
-    Ps[warp * AT_KT + lane] = p;
+      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      lrun[r] = lrun[r] * corr + ps;
+      mrun[r] = mnew;
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[r][e] *= corr;
+      Ps[(row0 + r) * AT_KT + lane] = p;
+    }
     __syncwarp();
     const int kmax = min(AT_KT, len - k0);
     if (kmax == AT_KT) {
-      float a2[DPL];
+      float a2[R][DPL];
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) a2[e] = 0.f;
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) a2[r][e] = 0.f;
 #pragma unroll
       for (int kk = 0; kk < AT_KT; kk += 2) {            // fully unrolled, two accumulator sets
-        const float p0 = Ps[warp * AT_KT + kk], p1 = Ps[warp * AT_KT + kk + 1];
+        float v0[DPL], v1[DPL];
 #pragma unroll
-        for (int e = 0; e < DPL; ++e) {
-          acc[e] = fmaf(p0, Vs[kk * KS + lane + 32 * e], acc[e]);
-          a2[e] = fmaf(p1, Vs[(kk + 1) * KS + lane + 32 * e], a2[e]);
+        for (int e = 0; e < DPL; ++e) { v0[e] = Vs[kk * KS + lane + 32 * e]; v1[e] = Vs[(kk + 1) * KS + lane + 32 * e]; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float p0 = Ps[(row0 + r) * AT_KT + kk], p1 = Ps[(row0 + r) * AT_KT + kk + 1];
+#pragma unroll
+          for (int e = 0; e < DPL; ++e) {
+            acc[r][e] = fmaf(p0, v0[e], acc[r][e]);
+            a2[r][e] = fmaf(p1, v1[e], a2[r][e]);
+          }
         }
       }
 #pragma unroll
-      for (int e = 0; e < DPL; ++e) acc[e] += a2[e];
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[r][e] += a2[r][e];
     } else {
       for (int kk = 0; kk < kmax; ++kk) {
-        const float pk = Ps[warp * AT_KT + kk];
 #pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[e] = fmaf(pk, Vs[kk * KS + lane + 32 * e], acc[e]);
+        for (int r = 0; r < R; ++r) {
+          const float pk = Ps[(row0 + r) * AT_KT + kk];
+#pragma unroll
+          for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(pk, Vs[kk * KS + lane + 32 * e], acc[r][e]);
+        }
       }
     }
-    for (int m = 0; m < nrel; ++m) {
-      const int kk = qi + m - window - k0;
-      if (kk >= 0 && kk < kmax) {
-        const float pk = Ps[warp * AT_KT + kk];
 #pragma unroll
-        for (int e = 0; e < DPL; ++e) acc[e] = fmaf(pk, Rv[m * KS + lane + 32 * e], acc[e]);
+    for (int r = 0; r < R; ++r) {
+      const int qi = q0 + row0 + r;
+      for (int m = 0; m < nrel; ++m) {
+        const int kk = qi + m - window - k0;
+        if (kk >= 0 && kk < kmax) {
+          const float pk = Ps[(row0 + r) * AT_KT + kk];
+#pragma unroll
+          for (int e = 0; e < DPL; ++e) acc[r][e] = fmaf(pk, Rv[m * KS + lane + 32 * e], acc[r][e]);
+        }
       }
     }
-    __syncthreads();   // tile buffer (kt&1) and Ps fully consumed before the next prefetch overwrites them
+    __syncthreads();   // tile buffer and Ps fully consumed before the next prefetch overwrites them
   }
   timeline_stamp(-13);
-  if (qi < len) {
-    const float inv = 1.f / lrun;
 #pragma unroll
-    for (int e = 0; e < DPL; ++e) {
-      const float o = acc[e] * inv;
-      const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
-      out[idx] = o;
-      if (p_hi) {
-        __nv_bfloat16 hb, lb;
-        split_bf16(o, hb, lb);
-        p_hi[idx] = hb;
-        p_lo[idx] = lb;
+  for (int r = 0; r < R; ++r) {
+    const int qi = q0 + row0 + r;
+    if (qi < len) {
+      const float inv = 1.f / lrun[r];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) {
+        const float o = acc[r][e] * inv;
+        const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
+        out[idx] = o;
+        if (p_hi) {
+          __nv_bfloat16 hb, lb;
+          split_bf16(o, hb, lb);
+          p_hi[idx] = hb;
+          p_lo[idx] = lb;
+        }
       }
     }
   }
