@@ -355,9 +355,11 @@ def pqmf_synthesis_filter(subbands=4, taps=62, cutoff_ratio=0.15, beta=9.0):
     return torch.from_numpy(hs).float().unsqueeze(0)
 
 
-def decoder_trunk(z, w, cfg):
-    """conv_pre + upsample/MRF stages: models.py:1024-1036 (same trunk as Generator :873-885)."""
+def decoder_trunk(z, w, cfg, g=None):
+    """conv_pre + upsample/MRF stages: models.py:1024-1036 (same trunk as Generator :873-885, which also adds cond(g))."""
     x = conv(z, w, "dec.conv_pre", padding=3)
+    if g is not None and "dec.cond.weight" in w:
+        x = x + conv(g, w, "dec.cond")                     # Generator.forward models.py:874-875
     nk = len(cfg["resblock_kernel_sizes"])
     rb = resblock1 if cfg["resblock"] == "1" else resblock2
     for i, (u, ku) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
@@ -400,9 +402,9 @@ def decoder_mb_istft(z, w, cfg):
     return wav, y_mb
 
 
-def decoder_hifigan(z, w, cfg):
-    """models.py:872-891 (plain HiFi-GAN Generator; g is ignored when cond is absent)."""
-    x = decoder_trunk(z, w, cfg)
+def decoder_hifigan(z, w, cfg, g=None):
+    """models.py:872-891 (plain HiFi-GAN Generator)."""
+    x = decoder_trunk(z, w, cfg, g)
     x = F.leaky_relu(x)
     x = conv(x, w, "dec.conv_post", padding=3)
     return torch.tanh(x), None
@@ -438,7 +440,7 @@ def infer(w, cfg, tokens, lengths, sid, scales, eps_dp, eps_z=None, return_all=F
     if cfg["decoder"] == "mb_istft":
         o, o_mb = decoder_mb_istft(zin, w, cfg)
     else:
-        o, o_mb = decoder_hifigan(zin, w, cfg)
+        o, o_mb = decoder_hifigan(zin, w, cfg, g)
     res = dict(o=o, o_mb=o_mb, w_ceil=w_ceil, y_lengths=y_lengths, idx=idx)
     if return_all:
         res.update(x=x, m_p=m_p, logs_p=logs_p, logw=logw, z_p=z_p, z=z, attn=attn, y_mask=y_mask, g=g)

@@ -208,6 +208,36 @@ def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
     e.close()
 
 
+def test_plain_hifigan_resblock2_variant_vs_oracle(cfg):
+    """Config-driven variant: plain HiFi-GAN `Generator` tail (conv_post + tanh, speaker projection added to conv_pre,
+    models.py:845-898) with ResBlock2 (modules.py:234-258), three upsampling stages 8x8x4.  The reference's own `infer`
+    cannot drive this decoder (`o, o_mb = self.dec(...)` at models.py:1703 fails to unpack the single tensor it returns),
+    so the engine is compared with the oracle restatement only (fp32 path)."""
+    import copy
+    from oracle import vits_oracle as vo
+    from vosk_tts_b200 import synthetic, weights
+    from vosk_tts_b200.engine import Engine
+    c2 = copy.deepcopy(cfg)
+    c2.update(decoder="hifigan", resblock="2", resblock_kernel_sizes=[3, 5, 7], resblock_dilation_sizes=[[1, 2], [2, 6], [3, 9]],
+              upsample_rates=[8, 8, 4], upsample_kernel_sizes=[16, 16, 8], upsample_initial_channel=256, n_layers=3)
+    folded = weights.fold_weight_norm(synthetic.make_random_checkpoint(c2, 77))
+    blob, man = weights.pack(folded, c2)
+    e = Engine(c2, blob, man, device=0, precision=0)
+    assert e.hop == 256
+    g = torch.Generator().manual_seed(5)
+    T = 40
+    tok = torch.randint(0, 62, (1, T), generator=g)
+    e1, e2 = torch.randn(1, 2, T, generator=g), torch.randn(1, 192, 24 * T, generator=g)
+    with torch.no_grad():
+        o = vo.infer(folded, c2, tok, torch.tensor([T]), torch.tensor([4]), (0.8, 1.0, 0.8), e1, e2)
+    ylen, dur = e.durations(tok.numpy(), [T], [4], (0.8, 1.0, 0.8), e1.numpy(), want_durations=True)
+    assert np.array_equal(dur[0], o["w_ceil"][0, 0].numpy().astype(np.int32))
+    Ty = int(ylen[0])
+    wav = e.synthesize(ylen, e2[:, :, :Ty].numpy())
+    assert np.abs(wav[0, : Ty * 256] - o["o"][0, 0].numpy()).max() < 2e-5
+    e.close()
+
+
 def test_fused_infer_equals_two_phase_and_handles_capacity(engine, cfg):
     """vtts_infer (one ABI call) == vtts_durations + vtts_synthesize; a too-small capacity falls back cleanly."""
     ids, lens, sid = _rand_batch(cfg, 3, 20, 45, 31)

@@ -138,7 +138,7 @@ struct vtts_engine {
   bool has_g = false;
   const float *emb_g = nullptr, *cond_w = nullptr, *cond_b = nullptr, *enc_emb = nullptr, *dp_ea = nullptr;
   const float *istft_basis = nullptr, *pqmf = nullptr;
-  int condR = 0, r_spk = -1, r_dp = 0, r_flow = 0;
+  int condR = 0, r_spk = -1, r_dp = 0, r_flow = 0, r_dec = -1;
   std::vector<EncLayerW> enc;
   ConvW enc_proj, dp_pre, dp_proj, dec_pre, dec_post;
   DdsW dp_dds[3];
@@ -448,6 +448,9 @@ void vtts_engine::bind_weights() {
     if (c.spk_cond_encoder) { r_spk = r; r += H; }
     r_dp = r; r += D;
     r_flow = r; r += nf * nl * 2 * H;
+    if (c.decoder_type == 1 && tensors.count("cond.w") && tensors["cond.w"].n == (size_t)(r + c.upsample_initial_channel) * G) {
+      r_dec = r; r += c.upsample_initial_channel;      // plain Generator: x = conv_pre(z) + cond(g)  (models.py:874-875)
+    }
     condR = r;
     cond_w = vec("cond.w", (size_t)condR * G);
     cond_b = vec("cond.b", condR);
@@ -1380,7 +1383,11 @@ void vtts_engine::decode(float* z, const int* fl, const int* fo) {
   }
   int ch = c.upsample_initial_channel;
   float* cur = ensure(d_d0, F * ch);
-  launch_conv({mk(dec_pre, z, I, 0, cur, ch, 0, 1, 3)}, 1, fl, fo, maxFrm, B);
+  {
+    ConvP p = mk(dec_pre, z, I, 0, cur, ch, 0, 1, 3);
+    if (has_g && r_dec >= 0) { p.cond = d_condv.p + r_dec; p.cond_ld = condR; }
+    launch_conv({p}, 1, fl, fo, maxFrm, B);
+  }
   int rm = 1;
   const int nk = c.n_resblock_kernels, nd = c.n_resblock_dilations;
   if ((int)d_stage.size() < c.n_upsamples) {

@@ -114,7 +114,12 @@ def _spec(cfg):
 
     # --- decoder (models.py:974-1063 / 845-898, modules.py:187-258)
     C0 = cfg["upsample_initial_channel"]
-    conv("dec.conv_pre", C0, I, 7, wn=True, gain=1.0)
+    if cfg["decoder"] == "mb_istft":
+        conv("dec.conv_pre", C0, I, 7, wn=True, gain=1.0)
+    else:      # plain Generator: conv_pre is not weight-normed and a speaker projection is added to its output (models.py:851,869-875)
+        conv("dec.conv_pre", C0, I, 7, wn=False, gain=1.0)
+        if G > 0:
+            conv("dec.cond", C0, G, 1, gain=0.5)
     ch = C0
     for i, (u, ku) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
         conv("dec.ups.%d" % i, ch // 2, ch, ku, wn=True, gain=1.0, transposed=True)
@@ -132,7 +137,7 @@ def _spec(cfg):
         conv("dec.subband_conv_post", cfg["subbands"] * (cfg["gen_istft_n_fft"] + 2), ch, 7,
              wn=True, bias=False, gain=0.25)
     else:
-        conv("dec.conv_post", 1, ch, 7, wn=True, bias=False, gain=0.5)
+        conv("dec.conv_post", 1, ch, 7, wn=False, bias=False, gain=0.5)     # plain Conv1d (models.py:868)
     return out
 
 

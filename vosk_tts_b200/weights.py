@@ -216,6 +216,9 @@ def pack(w, cfg, tc=True):
             for i in range(nl):
                 rows_w.append(cw[i * 2 * H:(i + 1) * 2 * H][il])
                 rows_b.append(cb[i * 2 * H:(i + 1) * 2 * H][il])
+        if cfg["decoder"] != "mb_istft" and "dec.cond.weight" in w:
+            rows_w.append(g("dec.cond.weight")[:, :, 0])       # Generator's speaker projection (models.py:869-875)
+            rows_b.append(g("dec.cond.bias"))
         P.add("cond.w", np.concatenate(rows_w, 0))
         P.add("cond.b", np.concatenate(rows_b, 0))
 
