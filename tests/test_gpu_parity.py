@@ -178,9 +178,9 @@ def test_graph_replay_equals_eager(engine, cfg):
 
 
 @pytest.mark.parametrize("env", [{"VTTS_TC_BN": "128"}, {"VTTS_TC_TALL": "1"}, {"VTTS_PDL": "1"}, {"VTTS_CONV_MAXS": "1", "VTTS_CONV_MAXG": "4"},
-                                 {"VTTS_ATTN_ROWS": "4"}],
+                                 {"VTTS_ATTN_ROWS": "4"}, {"VTTS_TC_MULTICAST": "1"}],
                          ids=["tc-128-wide-tiles", "tc-tall-activation-tiles", "programmatic-dependent-launch", "ffma-no-cluster-4-groups",
-                              "attention-4-rows-per-warp"])
+                              "attention-4-rows-per-warp", "tc-tma-multicast-cluster"])
 def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
     """The tuning switches select different tilings / launch modes of the same kernels (128-wide tcgen05 tiles are what
     batched calls use automatically); each must still reproduce the reference fixture."""

@@ -54,6 +54,7 @@ struct TcBatch {
                 //    UMMA descriptors; 0: a fresh 128-row tile per (chunk, tap)
   int a_bytes;  // bytes of one activation plane tile in shared memory (multiple of 1024)
   int baseoff;  // experiment: fill the descriptor base-offset field for row-shifted tiles
+  int cn;       // CTAs of a cluster along the channel-tile axis that share (TMA-multicast) one activation tile; 1 = off
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) for tuning (tools/microbench.py)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -69,6 +70,24 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
+}
+// TMA load whose box lands at the same shared-memory offset in every CTA of `mask` and signals each one's mbarrier
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -150,7 +169,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const int na = nsteps / a_per;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], (uint32_t)tb.cn); }
     for (int s = 0; s < TC_WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
     mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -167,6 +186,10 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int cn = tb.cn;
+  const uint32_t crank = cn > 1 ? cluster_rank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
+  if (cn > 1) cluster_sync_all();        // every peer's mbarriers exist before anybody multicasts into / arrives on them
   // everything above touched only this CTA's resources; from here on the producer kernel's results are needed
   PDL_WAIT();
   const int L = lens[b] * tb.rmul + P.in_extra;
@@ -189,8 +212,16 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           uint8_t* ab = smem + ast * 2 * A_BYTES;
           mbar_expect_tx(&a_full[ast], a_tx);
           const int row = (int)in_base + t0 - P.pad + (tall ? 0 : j * P.dil);
-          tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
-          tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
+          if (cn > 1) {
+            // this CTA fetches rows [crank, crank+1) * 128/cn of the tile and multicasts them to all cn CTAs
+            const int slice = TC_BM / cn;
+            const int soff = (int)crank * slice;
+            tma_load_2d_mc(ab + soff * 128, &P.a_hi, c * TC_BK, row + soff, &a_full[ast], cmask);
+            tma_load_2d_mc(ab + A_BYTES + soff * 128, &P.a_lo, c * TC_BK, row + soff, &a_full[ast], cmask);
+          } else {
+            tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
+            tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
+          }
         }
         const int wst = s % TC_WST, wuse = s / TC_WST;
         if (wuse > 0) mbar_wait(&w_empty[wst], (wuse - 1) & 1);
@@ -226,7 +257,10 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
         }
         umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
-        if ((s + 1) % a_per == 0) umma_commit(&a_empty[ast]);  // ... and the activation tile after its last tap
+        if ((s + 1) % a_per == 0) {                            // ... and the activation tile after its last tap
+          if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
+          else umma_commit(&a_empty[ast]);
+        }
         (void)c;
       }
       umma_commit(tmem_full);                 // accumulator complete
@@ -357,6 +391,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (threadIdx.x == 64) TC_STAMP(7);
   tc_fence_before();
   __syncthreads();
+  if (cn > 1) cluster_sync_all();        // no peer may still multicast into, or arrive on, this CTA's shared memory
   if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();

@@ -194,7 +194,7 @@ struct vtts_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = false;   // PDL measured slower inside graphs
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0;   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0;   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -612,13 +612,27 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   }
   if (BN == 128) tall = false;             // the 128-wide weight ring leaves no room for tall activation tiles
   if (!tall) maxNR = TC_BM;
+  // TMA multicast of the activation tile across the channel-tile CTAs of a cluster: only when every problem of the
+  // launch has the same number of channel tiles (no CTA of a cluster may drop out) and the tile is not "tall"
+  int cn = 1;
+  if (tc_mc && !tall) {
+    int ny = -1;
+    bool same = true;
+    for (const TcSpec& q : ps) {
+      const int n = (q.Cout + BN - 1) / BN;
+      if (ny < 0) ny = n; else if (n != ny) same = false;
+    }
+    if (same) cn = (ny % 4 == 0) ? 4 : (ny % 2 == 0 ? 2 : 1);
+    if (tc_mc == 2 && same && ny % 2 == 0) cn = 2;          // VTTS_TC_MULTICAST=2: pairs only
+  }
+  tb.cn = cn;
   tb.tall = tall ? 1 : 0;
   tb.baseoff = tc_baseoff;
   tb.a_bytes = (maxNR * 128 + 1023) / 1024 * 1024;
   for (size_t i = 0; i < ps.size(); ++i) {
     const TcSpec& q = ps[i];
     TcProblem& P = tb.p[i];
-    const int box_rows = tall ? TC_BM + (q.k - 1) * q.dil : TC_BM;
+    const int box_rows = tall ? TC_BM + (q.k - 1) * q.dil : TC_BM / cn;
     P.a_hi = make_map(q.in.hi, q.in.C, q.in.rows, box_rows);
     P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, box_rows);
     P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
@@ -652,8 +666,27 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     ++tc_prof_launches;
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
   }
-  if (BN == 128) klaunch(conv_tc_kernel<128>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes<128>(tb.a_bytes), tb, lens, offs);
-  else klaunch(conv_tc_kernel<64>, grid, dim3(TC_THREADS), (size_t)tc_smem_bytes<64>(tb.a_bytes), tb, lens, offs);
+  {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = dim3(TC_THREADS); lc.stream = stream;
+    lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes) : tc_smem_bytes<64>(tb.a_bytes);
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (cn > 1) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cn; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (use_pdl) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    lc.attrs = at; lc.numAttrs = na;
+    if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128>, tb, lens, offs));
+    else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64>, tb, lens, offs));
+  }
   CK(cudaGetLastError());
   if (profiling) {
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used + 1], stream));
@@ -1679,6 +1712,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
     if (const char* e = getenv("VTTS_TC_BN")) h->tc_bn = atoi(e);
+    if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
