@@ -23,8 +23,21 @@ namespace vtts {
 
 constexpr int TC_BM = 128;        // time rows per CTA (UMMA M)
 constexpr int TC_BK = 64;         // input channels per stage (one 128-byte swizzle atom of bf16)
-constexpr int TC_WST = 4;         // weight-tile ring depth (one tile per k-step)
-constexpr int TC_AST = 3;         // activation-tile ring depth (one tile per channel chunk, or per step when !tall)
+// ring depths per weight-tile width (BN): the 64-wide kernel has room for deeper rings than the 128-wide one
+#ifndef VTTS_TC_AST64
+#define VTTS_TC_AST64 3
+#endif
+#ifndef VTTS_TC_WST64
+#define VTTS_TC_WST64 4
+#endif
+#ifndef VTTS_TC_AST128
+#define VTTS_TC_AST128 3
+#endif
+#ifndef VTTS_TC_WST128
+#define VTTS_TC_WST128 4
+#endif
+template <int BN> constexpr int tc_ast() { return BN == 64 ? VTTS_TC_AST64 : VTTS_TC_AST128; }   // activation-tile ring depth
+template <int BN> constexpr int tc_wst() { return BN == 64 ? VTTS_TC_WST64 : VTTS_TC_WST128; }   // weight-tile ring depth
 constexpr int TC_THREADS = 192;
 constexpr int TC_MAXP = 4;
 
@@ -55,6 +68,9 @@ struct TcBatch {
   int a_bytes;  // bytes of one activation plane tile in shared memory (multiple of 1024)
   int baseoff;  // experiment: fill the descriptor base-offset field for row-shifted tiles
   int cn;       // CTAs of a cluster along the channel-tile axis that share (TMA-multicast) one activation tile; 1 = off
+  int split;    // cluster split-K: `split` CTAs (cluster dims (1,1,split)) each run a contiguous range of the k-steps of one
+                //    output tile, exchange partial accumulators through distributed shared memory and each finish
+                //    64/split of the tile's columns (reduce-scatter; fixed summation order => deterministic).  1 = off
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) for tuning (tools/microbench.py)
 };
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -132,19 +148,158 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- epilogue pieces shared by the plain and the split-K paths: EN accumulator columns starting at absolute column `cofs`
+template <int EN>
+__device__ __forceinline__ void tc_load_res(const TcProblem& P, float (&rr)[EN], int cofs, long orow, bool rowok) {
+  const bool gate = (P.epi & TCE_GATE) != 0;
+  const int ocb = gate ? (cofs >> 1) : cofs;
+  const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - cofs);
+  if (P.res && rowok && nvalid > 0) {
+    const float* rp = P.res + orow * (long)P.ldr + P.roff + ocb;
+#pragma unroll
+    for (int i = 0; i < EN; i += 4) {
+      if (i + 4 <= nvalid) {
+        const float4 q4 = *reinterpret_cast<const float4*>(rp + i);
+        rr[i] = q4.x; rr[i + 1] = q4.y; rr[i + 2] = q4.z; rr[i + 3] = q4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rr[i + e] = (i + e < nvalid) ? rp[i + e] : 0.f;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < EN; ++i) rr[i] = 0.f;
+  }
+}
+// v = accumulator + bias of EN columns; applies gate / relu / alpha / residual and stores fp32 rows and split-bf16 planes
+template <int EN>
+__device__ __forceinline__ void tc_finish_cols(const TcProblem& P, float (&v)[EN], const float (&rr)[EN], int cofs, long orow) {
+  const bool gate = (P.epi & TCE_GATE) != 0;
+  const bool relu = (P.epi & TCE_RELU) != 0;
+  const int ocb = gate ? (cofs >> 1) : cofs;           // first output channel of this pass
+  const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - cofs);
+  if (gate) {
+#pragma unroll
+    for (int i = 0; i < EN / 2; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
+  }
+#pragma unroll
+  for (int i = 0; i < EN; ++i) {
+    float u = v[i];
+    if (relu) u = fmaxf(u, 0.f);
+    v[i] = u * P.alpha + rr[i];
+  }
+  if (P.y) {
+    float* yr = P.y + orow * (long)P.ldy + P.yoff + ocb;
+    const bool al = ((P.ldy | P.yoff) & 3) == 0;
+#pragma unroll
+    for (int i = 0; i < EN; i += 4) {
+      if (al && i + 4 <= nvalid) {
+        *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (i + e < nvalid) yr[i + e] = v[i + e];
+      }
+    }
+  }
+  if (P.p_hi) {
+    __nv_bfloat16* ph = P.p_hi + orow * (long)P.ldp + P.poff + ocb;
+    __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + ocb;
+    const bool al = ((P.ldp | P.poff) & 7) == 0;
+#pragma unroll
+    for (int i = 0; i < EN; i += 8) {
+      __align__(16) __nv_bfloat16 hb[8], lb[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float u = v[i + e];
+        u = u > 0.f ? u : u * P.pl_slope;
+        split_bf16(u, hb[e], lb[e]);
+      }
+      if (al && i + 8 <= nvalid) {
+        *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb);
+        *reinterpret_cast<uint4*>(pl + i) = *reinterpret_cast<const uint4*>(lb);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (i + e < nvalid) { ph[i + e] = hb[e]; pl[i + e] = lb[e]; }
+      }
+    }
+  }
+}
+
+// Split-K tail of one epilogue thread (= one tile row).  The tile's BN columns are cut into SS slices of W = BN/SS;
+// slice q is finished by CTA q.  tc_split_send pushes the slices contained in one 64-column accumulator pass into the
+// owners' staging buffers [src CTA][row][W] (this CTA's own slice included, so no register array is indexed dynamically);
+// after the cluster barrier tc_split_finish adds the SS partials of its slice in rank order and runs the epilogue on them.
+template <int SS, int BN>
+__device__ __forceinline__ void tc_split_send(const float (&acc)[64], int half, float* stage, int sp, int row) {
+  constexpr int W = BN / SS;
+  constexpr int PER = 64 / W;              // slices inside one 64-column pass
+  const uint32_t mine = smem_u32(stage + ((size_t)sp * TC_BM + row) * W);
+#pragma unroll
+  for (int qq = 0; qq < PER; ++qq) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(mine), "r"(half * PER + qq));
+#pragma unroll
+    for (int i = 0; i < W; i += 4)
+      asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra + i * 4), "f"(acc[qq * W + i]), "f"(acc[qq * W + i + 1]),
+                   "f"(acc[qq * W + i + 2]), "f"(acc[qq * W + i + 3])
+                   : "memory");
+  }
+}
+template <int SS, int BN>
+__device__ __forceinline__ void tc_split_finish(const TcProblem& P, const float* stage, const float* bias_s, int sp, int row, int co0,
+                                                long orow, bool rowok) {
+  constexpr int W = BN / SS;
+  float rr[W];
+  tc_load_res<W>(P, rr, co0 + sp * W, orow, rowok);
+  cluster_sync_all();                      // (2) all partials have landed; nobody writes into a CTA after this point
+  float v[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] = 0.f;
+#pragma unroll
+  for (int src = 0; src < SS; ++src) {
+    const float4* sp4 = reinterpret_cast<const float4*>(stage + ((size_t)src * TC_BM + row) * W);
+#pragma unroll
+    for (int i = 0; i < W; i += 4) {
+      const float4 q4 = sp4[i >> 2];
+      v[i] += q4.x; v[i + 1] += q4.y; v[i + 2] += q4.z; v[i + 3] += q4.w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < W; ++i) v[i] += bias_s[sp * W + i];
+  if (rowok && co0 + sp * W < P.Cout) tc_finish_cols<W>(P, v, rr, co0 + sp * W, orow);
+}
+template <int SS, int BN, typename LoadAcc>
+__device__ __forceinline__ void tc_split_tail(const TcProblem& P, LoadAcc&& load_acc, float* stage, const float* bias_s, int sp, int row,
+                                              int co0, long orow, bool rowok) {
+  float v[64];
+  load_acc(0, v);
+  cluster_sync_all();                      // (1) every CTA of the cluster is done with its operand rings
+  tc_split_send<SS, BN>(v, 0, stage, sp, row);
+  if constexpr (BN == 128) {
+    load_acc(1, v);
+    tc_split_send<SS, BN>(v, 1, stage, sp, row);
+  }
+  tc_split_finish<SS, BN>(P, stage, bias_s, sp, row, co0, orow, rowok);
+}
+
 template <int BN>
 constexpr int tc_smem_bytes(int a_bytes) {
-  return TC_AST * 2 * a_bytes + TC_WST * 2 * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+  return tc_ast<BN>() * 2 * a_bytes + tc_wst<BN>() * 2 * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 }
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
   constexpr int B_BYTES = BN * TC_BK * 2;
+  constexpr int TC_AST = tc_ast<BN>(), TC_WST = tc_wst<BN>();
   PDL_LAUNCH();
   if (threadIdx.x == 0) TC_STAMP(0);
-  const int pi = blockIdx.z % tb.n;
-  const int b = blockIdx.z / tb.n;
+  const int S = tb.split;                              // cluster split-K ways; blockIdx.z = (b * n + problem) * S + rank
+  const int zi = blockIdx.z / S, sp = blockIdx.z - zi * S;
+  const int pi = zi % tb.n;
+  const int b = zi / tb.n;
   const TcProblem& P = tb.p[pi];
   const int co0 = blockIdx.y * BN;
   if (co0 >= P.Cout) return;
@@ -164,9 +319,9 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsteps = (P.Cin / TC_BK) * P.k;
-  const int a_per = tall ? P.k : 1;                    // k-steps sharing one activation tile
-  const int na = nsteps / a_per;
+  const int nsteps_all = (P.Cin / TC_BK) * P.k;
+  const int s_beg = (int)((long)nsteps_all * sp / S), s_end = (int)((long)nsteps_all * (sp + 1) / S);   // this CTA's k-steps
+  const int a_per = tall ? P.k : 1;                    // k-steps sharing one activation tile (tall => S == 1)
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], (uint32_t)tb.cn); }
@@ -190,7 +345,19 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const uint32_t crank = cn > 1 ? cluster_rank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
   if (cn > 1) cluster_sync_all();        // every peer's mbarriers exist before anybody multicasts into / arrives on them
-  // everything above touched only this CTA's resources; from here on the producer kernel's results are needed
+  // Weights are immutable: the first ring of weight tiles is requested before waiting for the producer of the activations.
+  const int w_pre = min(TC_WST, s_end - s_beg);
+  auto issue_w = [&](int s) {
+    const int c = s / P.k, j = s - c * P.k;
+    const int wst = (s - s_beg) % TC_WST;
+    uint8_t* wb = smem_w + wst * 2 * B_BYTES;
+    mbar_expect_tx(&w_full[wst], 2 * B_BYTES);
+    tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
+    tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
+  };
+  if (warp == 0 && lane == 0)
+    for (int i = 0; i < w_pre; ++i) issue_w(s_beg + i);
+  // everything above touched only this CTA's resources and constants; from here on the producer kernel's results are needed
   PDL_WAIT();
   const int L = lens[b] * tb.rmul + P.in_extra;
   const bool active = t0 < L;            // an idle CTA still has to release its TMEM columns below
@@ -199,15 +366,18 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (threadIdx.x == 0) TC_STAMP(1);
 
   if (!active) {
-    // nothing to compute
+    // nothing to compute; the prefetched weight tiles must have landed before this CTA's shared memory is released
+    if (warp == 0 && lane == 0)
+      for (int i = 0; i < w_pre; ++i) mbar_wait(&w_full[i], 0);
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t a_tx = 2u * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per tile pair
-      for (int s = 0; s < nsteps; ++s) {
+      for (int s = s_beg; s < s_end; ++s) {
         const int c = s / P.k, j = s - c * P.k;
-        if (s % a_per == 0) {
-          const int ai = s / a_per, ast = ai % TC_AST, use = ai / TC_AST;
+        const int ls = s - s_beg;                              // ring positions count this CTA's own steps
+        if (ls % a_per == 0) {
+          const int ai = ls / a_per, ast = ai % TC_AST, use = ai / TC_AST;
           if (use > 0) mbar_wait(&a_empty[ast], (use - 1) & 1);
           uint8_t* ab = smem + ast * 2 * A_BYTES;
           mbar_expect_tx(&a_full[ast], a_tx);
@@ -223,13 +393,12 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
             tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
           }
         }
-        const int wst = s % TC_WST, wuse = s / TC_WST;
-        if (wuse > 0) mbar_wait(&w_empty[wst], (wuse - 1) & 1);
-        uint8_t* wb = smem_w + wst * 2 * B_BYTES;
-        mbar_expect_tx(&w_full[wst], 2 * B_BYTES);
-        tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
-        tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
-        if (s == 0) TC_STAMP(2);
+        if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
+          const int wst = ls % TC_WST, wuse = ls / TC_WST;
+          mbar_wait(&w_empty[wst], (wuse - 1) & 1);
+          issue_w(s);
+        }
+        if (ls == 0) TC_STAMP(2);
       }
       TC_STAMP(3);
     }
@@ -237,13 +406,14 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
-      for (int s = 0; s < nsteps; ++s) {
+      for (int s = s_beg; s < s_end; ++s) {
         const int c = s / P.k, j = s - c * P.k;
-        const int ai = s / a_per, ast = ai % TC_AST;
-        if (s % a_per == 0) mbar_wait(&a_full[ast], (ai / TC_AST) & 1);
-        const int wst = s % TC_WST;
-        mbar_wait(&w_full[wst], (s / TC_WST) & 1);
-        if (s == 0) TC_STAMP(4);
+        const int ls = s - s_beg;
+        const int ai = ls / a_per, ast = ai % TC_AST;
+        if (ls % a_per == 0) mbar_wait(&a_full[ast], (ai / TC_AST) & 1);
+        const int wst = ls % TC_WST;
+        mbar_wait(&w_full[wst], (ls / TC_WST) & 1);
+        if (ls == 0) TC_STAMP(4);
         tc_fence_after();
         const uint32_t abase = smem_u32(smem + ast * 2 * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
         const uint32_t wbase = smem_u32(smem_w + wst * 2 * B_BYTES);
@@ -252,12 +422,12 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
 #pragma unroll
         for (int kk = 0; kk < TC_BK / 16; ++kk) {
           const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
-          umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (s | kk) ? 1u : 0u);
+          umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (ls | kk) ? 1u : 0u);
           umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
           umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
         }
         umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
-        if ((s + 1) % a_per == 0) {                            // ... and the activation tile after its last tap
+        if ((ls + 1) % a_per == 0) {                           // ... and the activation tile after its last tap
           if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
           else umma_commit(&a_empty[ast]);
         }
@@ -284,109 +454,53 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     const int t = t0 + quad * 32 + lane;
     const bool rowok = t < L;
     const long orow = out_base + (long)t * P.out_mul + P.out_add;
-    const bool gate = (P.epi & TCE_GATE) != 0;
-    const bool relu = (P.epi & TCE_RELU) != 0;
     constexpr int EN = 64;                                 // columns handled per epilogue pass
     float rr[EN];
-    auto load_res = [&](int eh) {                          // residual of pass `eh` (64 accumulator columns) into registers
-      const int co0e = co0 + eh * EN;
-      const int ocb = gate ? (co0e >> 1) : co0e;
-      const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - co0e);
-      if (P.res && rowok && nvalid > 0) {
-        const float* rp = P.res + orow * (long)P.ldr + P.roff + ocb;
-#pragma unroll
-        for (int i = 0; i < EN; i += 4) {
-          if (i + 4 <= nvalid) {
-            const float4 q4 = *reinterpret_cast<const float4*>(rp + i);
-            rr[i] = q4.x; rr[i + 1] = q4.y; rr[i + 2] = q4.z; rr[i + 3] = q4.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) rr[i + e] = (i + e < nvalid) ? rp[i + e] : 0.f;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < EN; ++i) rr[i] = 0.f;
-      }
-    };
-    load_res(0);
+    if (S == 1) tc_load_res<EN>(P, rr, co0, orow, rowok);
     asm volatile("bar.sync 1, 128;" ::: "memory");          // bias_s visible to the 4 epilogue warps
     mbar_wait(tmem_full, 0);
     if (threadIdx.x == 64) TC_STAMP(6);
     tc_fence_after();
+    auto load_acc = [&](int eh, float (&v)[EN]) {           // 64 accumulator columns of this thread's TMEM lane
+      uint32_t rg[EN];
+#pragma unroll
+      for (int n0 = 0; n0 < EN; n0 += 16) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(eh * EN + n0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
+              "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
+              "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
+            : "r"(taddr));
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < EN; ++i) v[i] = __uint_as_float(rg[i]);
+    };
+    if (S == 1) {
 #pragma unroll 1
-    for (int eh = 0; eh < BN / EN; ++eh) {
-      const int co0e = co0 + eh * EN;
-      if (co0e >= P.Cout) break;
-      if (eh > 0) load_res(eh);
-      const int ocb = gate ? (co0e >> 1) : co0e;           // first output channel of this pass
-      const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - co0e);
-      float v[EN];
-      {
-        uint32_t rg[EN];
+      for (int eh = 0; eh < BN / EN; ++eh) {
+        const int co0e = co0 + eh * EN;
+        if (co0e >= P.Cout) break;
+        if (eh > 0) tc_load_res<EN>(P, rr, co0e, orow, rowok);
+        float v[EN];
+        load_acc(eh, v);
 #pragma unroll
-        for (int n0 = 0; n0 < EN; n0 += 16) {
-          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(eh * EN + n0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
-                "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
-                "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
-              : "r"(taddr));
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < EN; ++i) v[i] = __uint_as_float(rg[i]) + bias_s[eh * EN + i];
+        for (int i = 0; i < EN; ++i) v[i] += bias_s[eh * EN + i];
+        if (rowok) tc_finish_cols<EN>(P, v, rr, co0e, orow);
       }
-      if (!rowok) continue;
-      if (gate) {
-#pragma unroll
-        for (int i = 0; i < EN / 2; ++i) v[i] = tanhf(v[2 * i]) * (1.f / (1.f + expf(-v[2 * i + 1])));
-      }
-#pragma unroll
-      for (int i = 0; i < EN; ++i) {
-        float u = v[i];
-        if (relu) u = fmaxf(u, 0.f);
-        v[i] = u * P.alpha + rr[i];
-      }
-      if (P.y) {
-        float* yr = P.y + orow * (long)P.ldy + P.yoff + ocb;
-        const bool al = ((P.ldy | P.yoff) & 3) == 0;
-#pragma unroll
-        for (int i = 0; i < EN; i += 4) {
-          if (al && i + 4 <= nvalid) {
-            *reinterpret_cast<float4*>(yr + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (i + e < nvalid) yr[i + e] = v[i + e];
-          }
-        }
-      }
-      if (P.p_hi) {
-        __nv_bfloat16* ph = P.p_hi + orow * (long)P.ldp + P.poff + ocb;
-        __nv_bfloat16* pl = P.p_lo + orow * (long)P.ldp + P.poff + ocb;
-        const bool al = ((P.ldp | P.poff) & 7) == 0;
-#pragma unroll
-        for (int i = 0; i < EN; i += 8) {
-          __align__(16) __nv_bfloat16 hb[8], lb[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float u = v[i + e];
-            u = u > 0.f ? u : u * P.pl_slope;
-            split_bf16(u, hb[e], lb[e]);
-          }
-          if (al && i + 8 <= nvalid) {
-            *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb);
-            *reinterpret_cast<uint4*>(pl + i) = *reinterpret_cast<const uint4*>(lb);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              if (i + e < nvalid) { ph[i + e] = hb[e]; pl[i + e] = lb[e]; }
-          }
-        }
-      }
+    } else {
+      float* stage = reinterpret_cast<float*>(smem);       // [S][128][BN/S] fp32 (32 or 64 KB), aliases the activation ring
+      const int row = quad * 32 + lane;
+      if (S == 2) tc_split_tail<2, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
+      else if (S == 4) tc_split_tail<4, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
+      else tc_split_tail<8, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
     }
+  }
+  if (S > 1 && active && warp < 2) {       // the producer and MMA warps take part in the two split-K cluster barriers
+    __syncwarp();
+    cluster_sync_all();
+    cluster_sync_all();
   }
   if (threadIdx.x == 64) TC_STAMP(7);
   tc_fence_before();

@@ -193,8 +193,9 @@ struct vtts_engine {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
-  bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = false;   // PDL measured slower inside graphs
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0;   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
+  bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2;
+  int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -611,6 +612,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     maxNR = std::max(maxNR, nr);
   }
   if (BN == 128) tall = false;             // the 128-wide weight ring leaves no room for tall activation tiles
+  if (tall && tc_smem_bytes<64>((maxNR * 128 + 1023) / 1024 * 1024) > 227 * 1024) tall = false;
   if (!tall) maxNR = TC_BM;
   // TMA multicast of the activation tile across the channel-tile CTAs of a cluster: only when every problem of the
   // launch has the same number of channel tiles (no CTA of a cluster may drop out) and the tile is not "tall"
@@ -625,6 +627,38 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     if (same) cn = (ny % 4 == 0) ? 4 : (ny % 2 == 0 ? 2 : 1);
     if (tc_mc == 2 && same && ny % 2 == 0) cn = 2;          // VTTS_TC_MULTICAST=2: pairs only
   }
+  // Cluster split-K for launches that leave most SMs idle (single utterances): S CTAs share the k-steps of one tile.
+  // The widest split whose clusters are all co-resident wins; 128-wide channel tiles are taken when they allow a
+  // wider split than 64-wide ones (same k-steps per CTA-step, half the CTAs per tile row).
+  int split = 1;
+  if (!tall && tc_split != 1) {
+    const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+    long active[2] = {0, 0};
+    int minsteps = 1 << 30;
+    bool wide = true;
+    for (const TcSpec& q : ps) {
+      minsteps = std::min(minsteps, q.Cin / TC_BK * q.k);
+      if (q.Cout < 128) wide = false;
+      for (int b = 0; b < nB; ++b) {
+        const long rt = (hl[b] * rmul + q.in_extra + TC_BM - 1) / TC_BM;
+        active[0] += rt * ((q.Cout + 63) / 64);
+        active[1] += rt * ((q.Cout + 127) / 128);
+      }
+    }
+    const int cap = tc_split > 1 ? tc_split : 8;
+    auto best = [&](int wi) {
+      for (int S = 8, si = 2; S >= 2; S >>= 1, --si)
+        if (S <= cap && minsteps >= tc_min_steps * S && active[wi] * S <= (long)tc_cluster_cap[wi][si] * S) return S;
+      return 1;
+    };
+    if (tc_bn == 64 || tc_bn == 128) split = best(tc_bn == 128);
+    else if (BN == 64) {
+      const int s64 = best(0), s128 = wide ? best(1) : 1;
+      if (s128 > s64) { BN = 128; split = s128; } else split = s64;
+    }
+  }
+  if (split > 1) cn = 1;
+  tb.split = split;
   tb.cn = cn;
   tb.tall = tall ? 1 : 0;
   tb.baseoff = tc_baseoff;
@@ -652,7 +686,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.n = (int)ps.size();
   tb.rmul = rmul;
   tb.dbg = tc_dbg;
-  dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n);
+  dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n * split);
   if (grid.x == 0) return;
   if (profiling) {
     if (tc_prof_used + 2 > tc_prof_ev.size()) {
@@ -673,9 +707,9 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes) : tc_smem_bytes<64>(tb.a_bytes);
     cudaLaunchAttribute at[2];
     int na = 0;
-    if (cn > 1) {
+    if (cn > 1 || split > 1) {
       at[na].id = cudaLaunchAttributeClusterDimension;
-      at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cn; at[na].val.clusterDim.z = 1;
+      at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cn; at[na].val.clusterDim.z = split;
       ++na;
     }
     if (use_pdl) {
@@ -921,7 +955,7 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   for (const ConvP& q : ps)
     for (int b = 0; b < nB; ++b) base0 += (long)((hl0[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
   // few tiles (batch 1): one 128-thread group per CTA and the k-steps spread over a cluster; many tiles: 4 groups per CTA
-  int G = base0 >= 2 * 148 ? conv_max_g : 1;
+  int G = base0 >= 2 * 148 ? conv_max_g : conv_min_g;
   for (const ConvP& q : ps) {
     while (G > 1 && q.Cin % (CV_CK * G) != 0) G >>= 1;
   }
@@ -1691,8 +1725,27 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<64>(24 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
       CK(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
+      for (int wi = 0; wi < 2; ++wi)
+        for (int si = 0; si < 3; ++si) {
+          const int S = 2 << si;
+          cudaLaunchConfig_t lc;
+          memset(&lc, 0, sizeof(lc));
+          lc.gridDim = dim3(1, 1, S * 64); lc.blockDim = dim3(TC_THREADS);
+          lc.dynamicSmemBytes = wi ? tc_smem_bytes<128>(16 * 1024) : tc_smem_bytes<64>(16 * 1024);
+          cudaLaunchAttribute at[1];
+          at[0].id = cudaLaunchAttributeClusterDimension;
+          at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = S;
+          lc.attrs = at; lc.numAttrs = 1;
+          int nc = 0;
+          cudaError_t e = wi ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<128>, &lc) : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<64>, &lc);
+          if (e != cudaSuccess) { nc = 0; cudaGetLastError(); }
+          h->tc_cluster_cap[wi][si] = nc;
+        }
+      if (getenv("VTTS_VERBOSE"))
+        fprintf(stderr, "[vtts] co-resident conv_tc clusters: BN64 %d/%d/%d  BN128 %d/%d/%d (S=2/4/8)\n", h->tc_cluster_cap[0][0], h->tc_cluster_cap[0][1],
+                h->tc_cluster_cap[0][2], h->tc_cluster_cap[1][0], h->tc_cluster_cap[1][1], h->tc_cluster_cap[1][2]);
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
@@ -1713,6 +1766,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
     if (const char* e = getenv("VTTS_TC_BN")) h->tc_bn = atoi(e);
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
+    if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
+    if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
+    if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;

@@ -30,8 +30,12 @@ __device__ __forceinline__ void timeline_stamp(int line) {
     if (i < 4000) { tl[1 + 2 * i] = (unsigned long long)line; tl[2 + 2 * i] = t; }
   }
 }
-#define PDL_LAUNCH() do { timeline_stamp(__LINE__); asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); } while (0)
-#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+// The trigger comes AFTER the wait: a kernel that triggered at entry would let its successor start, trigger in turn, and
+// so on -- inside a CUDA graph the whole chain piles onto the SMs spinning in griddepcontrol.wait (measured: slower).
+// Triggering after the wait keeps exactly one successor in flight: its launch latency and prologue overlap this
+// kernel's main work.
+#define PDL_LAUNCH() timeline_stamp(__LINE__)
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
 
 // ---- mbarrier / bulk-async-copy wrappers (shared by the tcgen05 conv and the DDS kernel)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -817,7 +821,8 @@ __device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, i
 __global__ void __launch_bounds__(256)
 dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restrict__ offs) {
   PDL_LAUNCH();
-  PDL_WAIT();
+  // token lengths/offsets are uploaded by host copies ordered before the graph, never produced by a predecessor kernel:
+  // they (and the immutable weights) may be touched before PDL_WAIT
   const int b = blockIdx.y;
   const int len = lens[b];
   const int t0 = blockIdx.x * DDS_TT;
@@ -847,6 +852,7 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
 #pragma unroll
   for (int i = 0; i < DDS_NS - 1; ++i)
     if (i < nch) issue_chunk(i);
+  PDL_WAIT();                                        // P.x comes from the previous kernel
 
   float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
   const int half = (P.k - 1) / 2;

@@ -55,7 +55,7 @@ def load_library(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB
+    path = os.environ.get("VTTS_LIB") or _build.LIB       # VTTS_LIB: load an alternative build (kernel A/B experiments)
     if not os.path.exists(path):
         if not build_if_missing:
             raise RuntimeError("libvtts.so is missing: run `python -m vosk_tts_b200.build`")
