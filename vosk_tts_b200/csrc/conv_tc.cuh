@@ -346,7 +346,11 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
   if (cn > 1) cluster_sync_all();        // every peer's mbarriers exist before anybody multicasts into / arrives on them
   // Weights are immutable: the first ring of weight tiles is requested before waiting for the producer of the activations.
-  const int w_pre = min(TC_WST, s_end - s_beg);
+  // (lens/offs are final before any graph that reads them starts -- host copies or the previous phase's graph -- so the
+  //  peek below only decides whether prefetching is worth it: idle CTAs of ragged batches must not fetch and then drain
+  //  128 KB of weights; the authoritative read stays after the wait)
+  const bool peek_active = t0 < lens[b] * tb.rmul + P.in_extra;
+  const int w_pre = peek_active ? min(TC_WST, s_end - s_beg) : 0;
   auto issue_w = [&](int s) {
     const int c = s / P.k, j = s - c * P.k;
     const int wst = (s - s_beg) % TC_WST;
@@ -395,7 +399,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         }
         if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
           const int wst = ls % TC_WST, wuse = ls / TC_WST;
-          mbar_wait(&w_empty[wst], (wuse - 1) & 1);
+          if (wuse > 0) mbar_wait(&w_empty[wst], (wuse - 1) & 1);
           issue_w(s);
         }
         if (ls == 0) TC_STAMP(2);

@@ -23,6 +23,8 @@
 using namespace vtts;
 
 namespace {
+constexpr int CONV_SMEM_MAX = 160 * 1024;   // dynamic shared memory opt-in of conv_kernel<G>
+
 
 struct Tensor {
   const float* p = nullptr;
@@ -194,7 +196,7 @@ struct vtts_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
@@ -954,28 +956,35 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   long base0 = 0;
   for (const ConvP& q : ps)
     for (int b = 0; b < nB; ++b) base0 += (long)((hl0[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
-  // few tiles (batch 1): one 128-thread group per CTA and the k-steps spread over a cluster; many tiles: 4 groups per CTA
+  // many tiles (batched calls): 4 thread groups per CTA, no cluster.  Few tiles (batch 1): the k-steps of a tile are
+  // spread over a cluster of S CTAs until the launch fills ~1 wave of SMs; ranks that still have long k-loops then get
+  // 2-4 thread groups each (a lone warp per scheduler issues an FFMA only every other cycle).
   int G = base0 >= 2 * 148 ? conv_max_g : conv_min_g;
-  for (const ConvP& q : ps) {
+  for (const ConvP& q : ps)
     while (G > 1 && q.Cin % (CV_CK * G) != 0) G >>= 1;
-  }
-  int xw = (CV_TT + maxHalo + 7) / 8 * 8 + 1;
+  auto min_steps = [&](int g) {
+    int ms = 1 << 30;
+    for (const ConvP& q : ps) ms = (q.Cin % (CV_CK * g) != 0) ? 0 : std::min(ms, q.Cin / (CV_CK * g) * q.k);
+    return ms;
+  };
+  int S = 1;
+  while (S < conv_max_s && base0 * S < conv_target && S * 2 <= min_steps(G)) S *= 2;
+  const int xw = (CV_TT + maxHalo + 7) / 8 * 8 + 1;
+  auto smem_floats = [&](int g) {
+    const size_t pipe = (size_t)2 * CV_CK * g * xw + (size_t)CV_NS * CV_CK * g * CV_TC;
+    return (std::max(pipe, (size_t)(g - 1) * 32 * CV_THREADS) + 3) / 4 * 4 + (size_t)32 * CV_THREADS;
+  };
+  if (conv_auto_g && base0 < 2 * 148)
+    while (G * 2 <= conv_max_g && min_steps(G * 2) / S >= conv_auto_g && smem_floats(G * 2) * sizeof(float) <= (size_t)CONV_SMEM_MAX) G *= 2;
+  REQUIRE(smem_floats(G) * sizeof(float) <= (size_t)CONV_SMEM_MAX, VTTS_ERR_INVALID, "conv tile does not fit in shared memory");
+  cb.S = S;
   cb.xw = xw;
   const size_t pipe_floats = (size_t)2 * CV_CK * G * xw + (size_t)CV_NS * CV_CK * G * CV_TC;
-  const size_t red_floats = (size_t)G * 32 * CV_THREADS;
-  const size_t smem = std::max(pipe_floats, red_floats) * sizeof(float);
-  // cluster size: split the k-steps of every tile over S CTAs until the launch fills ~2 waves of SMs
-  const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
-  long base = 0;
-  int minSteps = 1 << 30;
-  for (const ConvP& q : ps) {
-    for (int b = 0; b < nB; ++b)
-      base += (long)((hl[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
-    minSteps = std::min(minSteps, q.Cin / (CV_CK * G) * q.k);
-  }
-  int S = 1;
-  while (S < conv_max_s && base * S < conv_target && S * 2 <= minSteps) S *= 2;
-  cb.S = S;
+  const size_t red_floats = (size_t)(G - 1) * 32 * CV_THREADS;
+  const size_t stage_off = (std::max(pipe_floats, red_floats) + 3) / 4 * 4;
+  cb.stage_off = (int)stage_off;
+  const size_t smem = (stage_off + (S > 1 ? (size_t)32 * CV_THREADS : 0)) * sizeof(float);
+  const std::vector<int>& hl = hl0;
   dim3 grid(((maxL + CV_TT - 1) / CV_TT) * S, (maxCout + CV_TC - 1) / CV_TC, nB * cb.n);
   if (grid.x == 0) return;
   if (profiling) {
@@ -1173,12 +1182,8 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, xb, y, L.ln2.g, L.ln2.b, (const float*)nullptr, va, condR, x, tl, to, H, px.hi, px.lo);
     ++launches;
   }
-  if (enc_on_tc) {
-    TcSpec q; q.in = px; q.w = tc_encproj; q.bias = enc_proj.b; q.Cin = H; q.Cout = 2 * I; q.y = stats; q.ldy = 2 * I;
-    launch_tc({q}, 1, tl, to, maxTok, B);
-  } else {
-    launch_conv({mk(enc_proj, x, H, 0, stats, 2 * I, 0, 1, 0)}, 1, tl, to, maxTok, B);
-  }
+  // (the prior projection enc_p.proj, models.py:323, is only needed by phase 2: it is enqueued at the end of this phase so
+  //  that it runs while the host picks up the utterance lengths)
   if (!capturing) CK(cudaEventRecord(ev[2], stream));
 
   // ---- stochastic duration predictor, reverse (models.py:56-63, 93-101)
@@ -1243,6 +1248,13 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     int* p_len = reinterpret_cast<int*>(ensure_pinned(h_pin_len, (size_t)(2 * B + 2) * sizeof(int)));
     CK(cudaMemcpyAsync(p_len, fl, B * sizeof(int), cudaMemcpyDeviceToHost, stream));
     CK(cudaMemcpyAsync(p_len + B, fo, (B + 1) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  }
+  // prior statistics m_p, logs_p (models.py:323-325): overlaps the host's round trip between the two phases
+  if (enc_on_tc) {
+    TcSpec q; q.in = px; q.w = tc_encproj; q.bias = enc_proj.b; q.Cin = H; q.Cout = 2 * I; q.y = stats; q.ldy = 2 * I;
+    launch_tc({q}, 1, tl, to, maxTok, B);
+  } else {
+    launch_conv({mk(enc_proj, x, H, 0, stats, 2 * I, 0, 1, 0)}, 1, tl, to, maxTok, B);
   }
 }
 
@@ -1768,6 +1780,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
+    if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
@@ -1785,9 +1798,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     CK(cudaFuncSetAttribute(attn_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(attn_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(attn_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CK(cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    CK(cudaFuncSetAttribute(conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
-    CK(cudaFuncSetAttribute(conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024));
+    CK(cudaFuncSetAttribute(conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+    CK(cudaFuncSetAttribute(conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
+    CK(cudaFuncSetAttribute(conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_MAX));
     CK(cudaStreamSynchronize(h->stream));
   });
 }

@@ -113,6 +113,7 @@ struct ConvP {
 };
 
 struct ConvBatch {
+  int stage_off;   // float offset of the split-K staging buffer [S][8/S][128] float4 in dynamic shared memory
   ConvP p[CV_MAXP];
   int n;
   int rmul;  // rows per length unit of the input (1, 4, 16 ...)
@@ -183,7 +184,9 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   const int n_pos = CV_TT + (k - 1) * dil;
   const int nchunks = P.Cin / CKS;
   const int nsteps = nchunks * k;
-  const int nmine = nsteps > rank ? (nsteps - rank + S - 1) / S : 0;   // my steps: rank, rank+S, ...
+  // my steps: a contiguous range, so that the k taps of a channel chunk reuse one staged input tile
+  const int s_beg = (int)((long)nsteps * rank / S), s_end = (int)((long)nsteps * (rank + 1) / S);
+  const int nmine = s_end - s_beg;
 
   float acc[4][8];
 #pragma unroll
@@ -234,7 +237,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
     }
   };
   auto issue_w = [&](int i) {            // i-th of my steps
-    const int s = rank + i * S;
+    const int s = s_beg + i;
     const int c = s / k, j = s - c * k;
     float* dst = Ws + (i % CV_NS) * CKS * CV_TC;
 #pragma unroll
@@ -260,21 +263,18 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   if (t0 >= L) return;                  // uniform over the cluster (pending cp.async into our own smem is harmless)
   in_base = (long)offs[b] * cb.rmul;
   out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
-  int xbuf = 0;        // Xs buffer holding chunk `ccur`
-  int ccur = -1;
+  int xbuf = 0;        // Xs buffer holding the chunk of the current step
+  bool pending = false; // xr holds the next chunk, not yet staged
   if (nmine > 0) {
-    ccur = rank / k;
-    load_x(ccur);
+    load_x(s_beg / k);
     store_x(0);
   }
   timeline_stamp(-21);
   for (int i = 0; i < nmine; ++i) {
-    const int s = rank + i * S;
+    const int s = s_beg + i;
     const int c = s / k, j = s - c * k;
-    // chunk needed by my next step (prefetch into registers while this step computes)
-    const int cnext = (i + 1 < nmine) ? (s + S) / k : c;
-    const bool fetch = cnext != c;
-    if (fetch) load_x(cnext);
+    // chunk needed by my next step (prefetch into registers while this step computes; fetching it earlier was measured slower)
+    if (i + 1 < nmine && (s + 1) / k != c) { load_x((s + 1) / k); pending = true; }
     cp_async_wait<CV_NS - 2>();
     __syncthreads();                       // W[i] (and a freshly stored X chunk) visible; ring slot (i-1)%NS free
     if (i + CV_NS - 1 < nmine) issue_w(i + CV_NS - 1);
@@ -294,9 +294,10 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
 #pragma unroll
         for (int n = 0; n < 8; ++n) acc[m][n] = fmaf(a[m], bb[n], acc[m][n]);
     }
-    if (fetch) {                            // other buffer was last read >= 1 barrier ago
+    if (pending && (s + 1) / k != c) {      // last tap of this chunk: stage the next one (that buffer was last read >= 1 barrier ago)
       store_x(xbuf ^ 1);
       xbuf ^= 1;
+      pending = false;
     }
   }
 
@@ -304,8 +305,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   timeline_stamp(-22);
   cp_async_wait<0>();
   __syncthreads();
-  float* red = smem;                                       // [G-1][32][128]
-  float* part = smem + (G - 1) * 32 * CV_THREADS;          // [32][128] this CTA's partial tile
+  float* red = smem;                                       // [G-1][32][128], aliases the (now idle) pipeline buffers
   if (G > 1) {
     if (grp > 0) {
 #pragma unroll
@@ -323,41 +323,45 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
           for (int n = 0; n < 8; ++n) acc[m][n] += red[(g2 * 32 + m * 8 + n) * CV_THREADS + ltid];
     }
   }
-  // ownership of the 4 x 2 (row, 4-column chunk) units of each thread among the S ranks
+  // A thread's 4 x 8 tile is 8 units of 4 channels (unit g = row m = g/2, half qh = g%2); unit g is finished by rank
+  // g*S/8.  Every rank PUSHES its partial units into the owners' staging buffers [src rank][unit][thread] (a region no
+  // pipeline buffer aliases, so peers still in their main loop are not disturbed); after one cluster barrier each owner
+  // adds the S partials of its units in rank order.
   int m_lo = 0, m_hi = 4, q_lo = 0, q_hi = 2;
   if (S > 1) {
+    const int ne4 = 8 / S;                                 // units per owner
+    float4* stage = reinterpret_cast<float4*>(smem + cb.stage_off);
     if (grp == 0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int n = 0; n < 8; ++n) part[(m * 8 + n) * CV_THREADS + ltid] = acc[m][n];
+      for (int g = 0; g < 8; ++g) {
+        const int owner = (g * S) >> 3, u = g & (ne4 - 1);
+        const uint32_t la = smem_u32(stage + ((rank * ne4 + u) * CV_THREADS + ltid));
+        uint32_t ra;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(owner));
+        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra), "f"(acc[g >> 1][(g & 1) * 4 + 0]),
+                     "f"(acc[g >> 1][(g & 1) * 4 + 1]), "f"(acc[g >> 1][(g & 1) * 4 + 2]), "f"(acc[g >> 1][(g & 1) * 4 + 3])
+                     : "memory");
+      }
     }
-    cluster_sync_all();
+    cluster_sync_all();                                    // all partials landed; nobody touches a peer after this
     if (S == 2) { m_lo = 2 * rank; m_hi = m_lo + 2; }
     else if (S == 4) { m_lo = rank; m_hi = rank + 1; }
     else { m_lo = rank >> 1; m_hi = m_lo + 1; q_lo = rank & 1; q_hi = q_lo + 1; }
     if (grp == 0) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          if (m >= m_lo && m < m_hi && q >= q_lo && q < q_hi) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int idx = (m * 8 + q * 4 + e) * CV_THREADS + ltid;
-              float pr[8];
-#pragma unroll
-              for (int r2 = 0; r2 < 8; ++r2) pr[r2] = r2 < S ? ld_dsmem(part + idx, r2) : 0.f;   // independent loads in flight
-              float v = 0.f;
-#pragma unroll
-              for (int r2 = 0; r2 < 8; ++r2) v += pr[r2];                                        // fixed summation order
-              acc[m][q * 4 + e] = v;
-            }
+      for (int g = 0; g < 8; ++g) {
+        if (((g * S) >> 3) == rank) {
+          const int u = g & (ne4 - 1);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r2 = 0; r2 < S; ++r2) {                 // fixed summation order
+            const float4 q4 = stage[(r2 * ne4 + u) * CV_THREADS + ltid];
+            v.x += q4.x; v.y += q4.y; v.z += q4.z; v.w += q4.w;
           }
+          acc[g >> 1][(g & 1) * 4 + 0] = v.x; acc[g >> 1][(g & 1) * 4 + 1] = v.y;
+          acc[g >> 1][(g & 1) * 4 + 2] = v.z; acc[g >> 1][(g & 1) * 4 + 3] = v.w;
         }
       }
     }
-    cluster_sync_all();                                    // nobody leaves while its smem may still be read
   }
   if (grp > 0) return;
   timeline_stamp(-23);
