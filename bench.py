@@ -332,7 +332,7 @@ def main():
         dom = "tc" if fam["tc"][0] > fam["ffma"][0] else "ffma"
         d_ms, d_fl, d_n = fam[dom]
         ach = d_fl / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
-        kname = {"tc": "conv_tc_kernel<64> (tcgen05 + TMA conv1d-as-GEMM, split-bf16 x3, fp32 accumulate in TMEM)",
+        kname = {"tc": "conv_tc_kernel<64, cluster split-K> (tcgen05 + TMA conv1d-as-GEMM, split-bf16 x3, fp32 accumulate in TMEM, DSMEM reduce-scatter)",
                  "ffma": "conv_kernel<G> (fp32 FFMA conv1d-as-GEMM, cluster split-K)"}[dom]
         other = "ffma" if dom == "tc" else "tc"
         o_ms, o_fl, o_n = fam[other]

@@ -690,6 +690,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.dbg = tc_dbg;
   dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n * split);
   if (grid.x == 0) return;
+  tb.wpre = (long)grid.x * grid.y * grid.z <= 148 ? 1 : 0;
   if (profiling) {
     if (tc_prof_used + 2 > tc_prof_ev.size()) {
       tc_prof_ev.resize(tc_prof_used + 2);
@@ -720,8 +721,15 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
       ++na;
     }
     lc.attrs = at; lc.numAttrs = na;
-    if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128>, tb, lens, offs));
-    else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64>, tb, lens, offs));
+    // single-wave launches all use the split-capable instantiation (also with split == 1): alternating between two kernel
+    // images costs instruction-cache misses on every launch of a latency-bound chain
+    if (split > 1 || tb.wpre) {
+      if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true>, tb, lens, offs));
+      else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true>, tb, lens, offs));
+    } else {
+      if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, false>, tb, lens, offs));
+      else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, false>, tb, lens, offs));
+    }
   }
   CK(cudaGetLastError());
   if (profiling) {
@@ -1737,8 +1745,10 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
       for (int wi = 0; wi < 2; ++wi)
         for (int si = 0; si < 3; ++si) {
           const int S = 2 << si;
@@ -1751,7 +1761,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
           at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = S;
           lc.attrs = at; lc.numAttrs = 1;
           int nc = 0;
-          cudaError_t e = wi ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<128>, &lc) : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<64>, &lc);
+          cudaError_t e = wi ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<128, true>, &lc) : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<64, true>, &lc);
           if (e != cudaSuccess) { nc = 0; cudaGetLastError(); }
           h->tc_cluster_cap[wi][si] = nc;
         }
