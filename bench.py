@@ -119,6 +119,18 @@ def host_cores():
     return n
 
 
+def ncu_traffic(family):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_conv_tc_traffic.json")
+    if family != "tc" or not os.path.exists(path):
+        return None
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch_mean"])
+    except Exception:
+        return None
+
+
 def pick_threads(cfg, w, cores):
     """PyTorch's intra-op pool is at its best well below the core count on these tiny convs (128 threads ran 300x
     slower than 8 on the B200 host): probe a short utterance at a few thread counts and keep the fastest, so that
@@ -358,7 +370,7 @@ def main():
                              "peak_source": pk["src"] + " cuBLAS bf16 (sustained). achieved = algorithmic FLOPs (2*Cin*k*Cout per output "
                              "position) / summed CUDA-event durations of the launches in the profiled pass; the split-bf16 kernel "
                              "issues 3 MMAs per algorithmic MAC, so its ceiling on this scale is peak/3",
-                             "traffic": None, "launches_per_step": d_n / max(args.steps, 1),
+                             "traffic": ncu_traffic(dom), "launches_per_step": d_n / max(args.steps, 1),
                              "share_of_step": d_ms / prof_total_ms if prof_total_ms else None,
                              "flops_per_step": d_fl / max(args.steps, 1),
                              "other_family": {"kernel": other, "ms_per_step": o_ms / max(args.steps, 1),
