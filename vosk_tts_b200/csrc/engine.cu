@@ -196,7 +196,7 @@ struct vtts_engine {
   std::unordered_map<uint64_t, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   float stage_ms[8] = {};
@@ -748,6 +748,22 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
   long rows = 0;
   for (int b = 0; b < B; ++b) rows += hl[b];
   const int R = (attn_rows == 1 || attn_rows == 4) ? attn_rows : (rows * cfg.n_heads >= 8L * 2 * 148 * 4 ? 4 : 1);
+  // single short utterances: split-KV variant (all K/V tiles resident, 4 warps per query row) when it fits one wave
+  {
+    long ctas = 0;
+    for (int b = 0; b < B; ++b) ctas += (long)((hl[b] + ATS_ROWS - 1) / ATS_ROWS) * cfg.n_heads;
+    const int mt = (maxLen + AT_KT - 1) / AT_KT;
+    if (attn_split && R == 1 && mt <= ATS_MAXT && ctas <= 148 && dk % 32 == 0 && dk <= 128) {
+      dim3 grid((maxLen + ATS_ROWS - 1) / ATS_ROWS, cfg.n_heads, B);
+      const size_t smem = (size_t)attn_split_smem_floats(dk, nrel, mt) * sizeof(float);
+#define ATTN_SPLIT(D) klaunch(attn_split_kernel<D>, grid, dim3(ATS_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, mt, lens, offs, ph, plo)
+      switch (dk / 32) { case 1: ATTN_SPLIT(1); break; case 2: ATTN_SPLIT(2); break; case 3: ATTN_SPLIT(3); break; default: ATTN_SPLIT(4); break; }
+#undef ATTN_SPLIT
+      CK(cudaGetLastError());
+      ++launches;
+      return;
+    }
+  }
   const int QT = 8 * R;
   dim3 grid((maxLen + QT - 1) / QT, cfg.n_heads, B);
   const size_t smem = (size_t)attn_smem_floats(dk, nrel, R) * sizeof(float);
@@ -1790,6 +1806,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
+    if (const char* e = getenv("VTTS_ATTN_SPLIT")) h->attn_split = atoi(e);       // 0: never use the split-KV attention
     if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
@@ -1800,6 +1817,10 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->bind_weights();
     h->build_prefetch_list();
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(attn_split_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CK(cudaFuncSetAttribute(attn_split_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(attn_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(attn_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CK(cudaFuncSetAttribute(attn_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

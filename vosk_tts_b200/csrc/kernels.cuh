@@ -763,6 +763,202 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split-KV variant of the attention for single short utterances (latency bound: a warp of attn_kernel walks all key
+// tiles of its row serially, ~1.8 us per tile).  One CTA = 4 query rows of one head, 16 warps; all K/V tiles of the utterance
+// (<= ATS_MAXT) are resident in shared memory; warp w handles row w%4 and the key tiles {w/4, w/4+4}; the four
+// partial (max, sum, accumulator) states of a row are merged in segment order at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int ATS_ROWS = 4, ATS_SEG = 4, ATS_MAXT = 8, ATS_WARPS = ATS_ROWS * ATS_SEG, ATS_THREADS = 32 * ATS_WARPS;
+constexpr int attn_split_smem_floats(int dk, int nrel, int ntiles) {
+  return 2 * ntiles * AT_KT * (dk + 4) + ATS_ROWS * (dk + 4) + 2 * nrel * (dk + 4) + ATS_ROWS * nrel + ATS_WARPS * AT_KT + ATS_WARPS * (4 + dk);
+}
+
+template <int DPL>  // dk = 32*DPL
+__global__ void __launch_bounds__(ATS_THREADS)
+attn_split_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
+                  const float* __restrict__ relv, int n_heads, int window, int max_tiles, const int* __restrict__ lens,
+                  const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+  PDL_LAUNCH();
+  constexpr int DK = 32 * DPL;
+  constexpr int KS = DK + 4;
+  const int b = blockIdx.z, head = blockIdx.y;
+  const int nrel = 2 * window + 1;
+  extern __shared__ __align__(16) float sm[];
+  float* KV = sm;                                   // [max_tiles][K | V][KT][KS]
+  float* Qs = KV + 2 * max_tiles * AT_KT * KS;      // [ROWS][KS]
+  float* Rk = Qs + ATS_ROWS * KS;                   // [nrel][KS]
+  float* Rv = Rk + nrel * KS;                       // [nrel][KS]
+  float* QE = Rv + nrel * KS;                       // [2][nrel]
+  float* Ps = QE + ATS_ROWS * nrel;                 // [8 warps][KT]
+  float* Mg = Ps + ATS_WARPS * AT_KT;               // [warps][4 + DK]  (m, l, -, -, acc[DK])
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // the relative-position tables are constants: staged before the dependency wait
+  for (int i = tid; i < nrel * (DK / 4); i += ATS_THREADS) {
+    const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+    *reinterpret_cast<float4*>(Rk + r * KS + d4) = *reinterpret_cast<const float4*>(relk + r * DK + d4);
+    *reinterpret_cast<float4*>(Rv + r * KS + d4) = *reinterpret_cast<const float4*>(relv + r * DK + d4);
+  }
+  PDL_WAIT();
+  const int len = lens[b];
+  const int q0 = blockIdx.x * ATS_ROWS;
+  if (q0 >= len) return;
+  const long base = offs[b];
+  const int HT = n_heads * DK;
+  const int ntiles = (len + AT_KT - 1) / AT_KT;     // <= max_tiles (host guarantees)
+
+  auto issue_tile = [&](int kt) {
+    float* kd = KV + kt * 2 * AT_KT * KS;
+    float* vd = kd + AT_KT * KS;
+    const int k0 = kt * AT_KT;
+    for (int i = tid; i < AT_KT * (DK / 4); i += ATS_THREADS) {
+      const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+      const int t = k0 + r;
+      const bool ok = t < len;
+      const float* rowp = qkv + (base + (ok ? t : 0)) * (long)ld + head * DK + d4;
+      cp_async16(kd + r * KS + d4, rowp + HT, ok ? 16 : 0);
+      cp_async16(vd + r * KS + d4, rowp + 2 * HT, ok ? 16 : 0);
+    }
+  };
+  // two commit groups: the tiles of the first round (0..3) and of the second (4..7)
+  for (int kt = 0; kt < min(ntiles, ATS_SEG); ++kt) issue_tile(kt);
+  cp_async_commit();
+  for (int kt = ATS_SEG; kt < ntiles; ++kt) issue_tile(kt);
+  cp_async_commit();
+
+  for (int i = tid; i < ATS_ROWS * (DK / 4); i += ATS_THREADS) {
+    const int r = i / (DK / 4), d4 = (i - r * (DK / 4)) * 4;
+    const int t = q0 + r;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < len) q = *reinterpret_cast<const float4*>(qkv + (base + t) * (long)ld + head * DK + d4);
+    const float sc = sqrtf((float)DK);
+    q.x /= sc; q.y /= sc; q.z /= sc; q.w /= sc;
+    *reinterpret_cast<float4*>(Qs + r * KS + d4) = q;
+  }
+  __syncthreads();
+  for (int i = tid; i < ATS_ROWS * nrel; i += ATS_THREADS) {
+    const int r = i / nrel, m = i - r * nrel;
+    float a = 0.f;
+#pragma unroll 4
+    for (int d4 = 0; d4 < DK; d4 += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(Qs + r * KS + d4);
+      const float4 e = *reinterpret_cast<const float4*>(Rk + m * KS + d4);
+      a = fmaf(q.x, e.x, a); a = fmaf(q.y, e.y, a); a = fmaf(q.z, e.z, a); a = fmaf(q.w, e.w, a);
+    }
+    QE[i] = a;
+  }
+
+  const int row = warp % ATS_ROWS, seg = warp / ATS_ROWS;
+  const int qi = q0 + row;
+  float mrun = -INFINITY, lrun = 0.f, acc[DPL];
+#pragma unroll
+  for (int e = 0; e < DPL; ++e) acc[e] = 0.f;
+  float* Pw = Ps + warp * AT_KT;
+
+#pragma unroll 1
+  for (int round = 0; round < 2; ++round) {
+    if (round == 0) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();                               // this round's tiles (and QE) visible to every warp
+    const int kt = seg + round * ATS_SEG;
+    if (kt >= ntiles) continue;                    // (uniform per warp; the barriers above are outside the branch)
+    const int k0 = kt * AT_KT;
+    const float* Ks = KV + kt * 2 * AT_KT * KS;
+    const float* Vs = Ks + AT_KT * KS;
+    const int key = k0 + lane;
+    const bool kvalid = key < len;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int d4 = 0; d4 < DK; d4 += 4) {
+      const float4 kd = *reinterpret_cast<const float4*>(Ks + lane * KS + d4);
+      const float4 qd = *reinterpret_cast<const float4*>(Qs + row * KS + d4);
+      s0 = fmaf(qd.x, kd.x, s0); s1 = fmaf(qd.y, kd.y, s1); s2 = fmaf(qd.z, kd.z, s2); s3 = fmaf(qd.w, kd.w, s3);
+    }
+    float sc = (s0 + s1) + (s2 + s3);
+    const int rel = key - qi + window;
+    if (rel >= 0 && rel < nrel) sc += QE[row * nrel + rel];
+    if (!kvalid) sc = -INFINITY;
+    float mx = sc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float mnew = fmaxf(mrun, mx);
+    const float corr = expf(mrun - mnew);
+    const float p = kvalid ? expf(sc - mnew) : 0.f;
+    float ps = p;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+    lrun = lrun * corr + ps;
+    mrun = mnew;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[e] *= corr;
+    Pw[lane] = p;
+    __syncwarp();
+    const int kmax = min(AT_KT, len - k0);
+    float a2[DPL];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) a2[e] = 0.f;
+    int kk = 0;
+    for (; kk + 1 < kmax; kk += 2) {
+      const float p0 = Pw[kk], p1 = Pw[kk + 1];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) {
+        acc[e] = fmaf(p0, Vs[kk * KS + lane + 32 * e], acc[e]);
+        a2[e] = fmaf(p1, Vs[(kk + 1) * KS + lane + 32 * e], a2[e]);
+      }
+    }
+    if (kk < kmax) {
+      const float p0 = Pw[kk];
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) acc[e] = fmaf(p0, Vs[kk * KS + lane + 32 * e], acc[e]);
+    }
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) acc[e] += a2[e];
+    for (int m = 0; m < nrel; ++m) {
+      const int kr = qi + m - window - k0;
+      if (kr >= 0 && kr < kmax) {
+        const float pk = Pw[kr];
+#pragma unroll
+        for (int e = 0; e < DPL; ++e) acc[e] = fmaf(pk, Rv[m * KS + lane + 32 * e], acc[e]);
+      }
+    }
+    __syncwarp();                                  // Pw is rewritten in the next round
+  }
+  // merge the four segments of each row (segment order => deterministic)
+  float* mg = Mg + warp * (4 + DK);
+  if (lane == 0) { mg[0] = mrun; mg[1] = lrun; }
+#pragma unroll
+  for (int e = 0; e < DPL; ++e) mg[4 + lane + 32 * e] = acc[e];
+  __syncthreads();
+  if (seg == 0 && qi < len) {
+    float mstar = -INFINITY;
+#pragma unroll
+    for (int g = 0; g < ATS_SEG; ++g) mstar = fmaxf(mstar, Mg[(row + ATS_ROWS * g) * (4 + DK)]);
+    float l = 0.f, o[DPL];
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) o[e] = 0.f;
+#pragma unroll
+    for (int g = 0; g < ATS_SEG; ++g) {
+      const float* pg = Mg + (row + ATS_ROWS * g) * (4 + DK);
+      const float w = expf(pg[0] - mstar);         // exp(-inf) = 0 for a segment that had no tile
+      l = fmaf(pg[1], w, l);
+#pragma unroll
+      for (int e = 0; e < DPL; ++e) o[e] = fmaf(pg[4 + lane + 32 * e], w, o[e]);
+    }
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int e = 0; e < DPL; ++e) {
+      const float v = o[e] * inv;
+      const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
+      out[idx] = v;
+      if (p_hi) {
+        __nv_bfloat16 hb, lb;
+        split_bf16(v, hb, lb);
+        p_hi[idx] = hb;
+        p_lo[idx] = lb;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // One DDSConv layer (modules.py:96-108): depthwise dilated conv k -> LN -> GELU(erf) -> 1x1 -> LN ->
 // GELU -> + x.  One CTA = 8 positions x all C channels (C == blockDim.x <= 256).
 // ------------------------------------------------------------------------------------------------
