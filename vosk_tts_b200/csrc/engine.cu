@@ -158,6 +158,7 @@ struct vtts_engine {
   EncodeFn encode_tiled = nullptr;
   Buf<__nv_bfloat16> pl_pool[128];            // plane buffers (hi/lo pairs), indexed by the decoder code
   unsigned long long* tc_dbg = nullptr;     // device stamps buffer (microbench)
+  TcBatch tc_batch;                         // launch_tc's parameter block (calls on one handle are serialised by `mu`)
   double tc_prof_flops = 0.0;
   uint64_t tc_prof_launches = 0;
   std::vector<cudaEvent_t> tc_prof_ev;
@@ -603,8 +604,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     if (tc_bn == 64 || tc_bn == 128) BN = tc_bn;
   }
   REQUIRE(!ps.empty() && (int)ps.size() <= TC_MAXP, VTTS_ERR_INVALID, "bad grouped tensor-core conv");
-  static TcBatch tbs;   // 2.6 KB: keep it off the stack frame of every caller
-  TcBatch& tb = tbs;
+  TcBatch& tb = tc_batch;   // per-engine scratch (2.6 KB: kept off the stack frame of every caller)
   memset(&tb, 0, sizeof(tb));
   int maxCout = 0, maxL = 0, maxNR = TC_BM;
   bool tall = tc_tall != 0;
