@@ -127,3 +127,34 @@ def reference_infer(net, tokens, lengths, sid, scales, eps_dp, eps_z_fn):
     finally:
         torch.randn, torch.randn_like = orig_randn, orig_randn_like
     return dict(o=o, o_mb=o_mb, attn=attn, y_mask=y_mask, z=z, z_p=z_p, m_p=m_p, logs_p=logs_p)
+
+
+def export_reference_onnx(path, net, n_vocab=62, opset=15):
+    """Write ``model.onnx`` for ``net`` the way the reference does (training/vits2/onnx_export.py:60-104): ``forward`` is
+    replaced by the infer wrapper, inputs ``input, input_lengths, scales, sid``, output ``output``, dynamic batch/time
+    axes, legacy TorchScript exporter.  The ``onnx`` python package is absent in this image; the exporter only imports
+    it for a post-processing step that attaches onnxscript functions (there are none here), which is bypassed."""
+    from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
+
+    def infer_forward(text, text_lengths, scales, sid=None):
+        return net.infer(text, text_lengths, noise_scale=scales[0], length_scale=scales[1], noise_scale_w=scales[2],
+                         sid=sid)[0].unsqueeze(1)
+
+    orig_fn, orig_forward = onnx_proto_utils._add_onnxscript_fn, net.forward
+    onnx_proto_utils._add_onnxscript_fn = lambda proto, custom_opsets: proto
+    net.forward = infer_forward
+    try:
+        g = torch.Generator().manual_seed(0)
+        text = torch.randint(0, n_vocab, (1, 50), dtype=torch.long, generator=g)
+        args = (text, torch.LongTensor([50]), torch.FloatTensor([0.667, 1.0, 0.8]), torch.LongTensor([0]))
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.onnx.export(model=net, args=args, f=str(path), verbose=False, opset_version=opset,
+                              input_names=["input", "input_lengths", "scales", "sid"], output_names=["output"],
+                              dynamic_axes={"input": {0: "batch_size", 1: "phonemes"}, "input_lengths": {0: "batch_size"},
+                                            "output": {0: "batch_size", 1: "time"}}, dynamo=False)
+    finally:
+        onnx_proto_utils._add_onnxscript_fn = orig_fn
+        net.forward = orig_forward
+    return path

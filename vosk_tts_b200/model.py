@@ -3,8 +3,9 @@
 Same constructor and attributes (`onnx`, `dic`, `config`, `tokenizer`); the model directory holds what the reference
 ships (`config.json`, `dictionary`) plus the checkpoint the ONNX graph was exported from (`G_*.pth` / `model.pth`,
 training/vits2/onnx_export.py:55) and, optionally, the training json (`vits_config.json`) when `config.json` has no
-`model` block.  Loading weights straight from `model.onnx` initialisers is a next-row item (no protobuf reader here);
-downloading models needs a network and is out of scope -- a missing model is an error, never a silent fallback.
+`model` block.  A directory that holds only what vosk-tts ships (`model.onnx`, `config.json`, `dictionary`) works too: the
+weights AND the architecture are read from the graph's initializers (`onnx_weights.py`, no `onnx` package needed).
+Downloading models needs a network and is out of scope -- a missing model is an error, never a silent fallback.
 """
 import glob
 import json
@@ -58,6 +59,17 @@ class Model:
         if session is not None:
             self.onnx = session
             return
+        cks = sorted(glob.glob(str(model_path / "G_*.pth")), key=lambda p: int(re.sub(r"\D", "", os.path.basename(p)) or 0))
+        if (model_path / "model.pth").exists():
+            cks.append(str(model_path / "model.pth"))
+        if not cks and (model_path / "model.onnx").exists():
+            # the deployed layout (vosk_tts/model.py:46): everything comes out of the graph
+            from . import onnx_weights as _onnx
+            sr = int(self.config.get("audio", {}).get("sample_rate", 22050))
+            cfg = _onnx.config_from_onnx(str(model_path / "model.onnx"), sampling_rate=sr)
+            folded = _onnx.state_dict_from_onnx(str(model_path / "model.onnx"))
+            self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision)
+            return
         if "model" in self.config and "data" in self.config:
             n_vocab = len(self.config.get("phoneme_id_map", {})) or 62
             cfg = _config.from_training_json(self.config, n_vocab=n_vocab)
@@ -66,12 +78,8 @@ class Model:
             cfg = _config.from_training_json(str(model_path / "vits_config.json"), n_vocab=n_vocab)
         else:
             cfg = _config.DEFAULT_CONFIG
-        cks = sorted(glob.glob(str(model_path / "G_*.pth")), key=lambda p: int(re.sub(r"\D", "", os.path.basename(p)) or 0))
-        if (model_path / "model.pth").exists():
-            cks.append(str(model_path / "model.pth"))
         if not cks:
-            raise FileNotFoundError("no checkpoint (G_*.pth / model.pth) in %s; model.onnx initialisers cannot be read by "
-                                    "this build" % model_path)
+            raise FileNotFoundError("no weights in %s: expected model.onnx (deployed layout) or G_*.pth / model.pth" % model_path)
         folded = _weights.load_checkpoint(cks[-1])
         self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision)
 

@@ -6,6 +6,7 @@ calls `self.model.onnx.run(None, args)[0]` (vosk_tts/synth.py:123-126).  `VitsSe
 `sid`; `bert` / `phone_duration_extra` must be None, synth.py:118-119) and returns
 `[float32 [B,1,1,T_wav]]` like the exported graph (onnx_export.py:65-72).
 """
+import logging
 import threading
 
 import numpy as np
@@ -20,6 +21,9 @@ class VitsSession:
         """state_dict: reference checkpoint `['model']` dict (weight_g/weight_v allowed) or already folded.
         packed: optional (blob, manifest) to skip packing (e.g. received through an NCCL broadcast)."""
         self.cfg = cfg or _config.DEFAULT_CONFIG
+        if precision > 0 and not _weights.tc_supported(self.cfg):
+            logging.warning("model widths are not multiples of 64: the tcgen05 conv path is unavailable, using the fp32 kernels")
+            precision = 0
         if packed is None:
             folded = _weights.fold_weight_norm(state_dict)
             packed = _weights.pack(folded, self.cfg)

@@ -157,10 +157,18 @@ def convt_phases(u, K):
     return phases
 
 
+def tc_supported(cfg):
+    """The tcgen05 conv path packs 64-channel K chunks: every conv it takes over must have Cin % 64 == 0."""
+    n_ups = len(cfg["upsample_rates"])
+    return (cfg["decoder"] == "mb_istft" and str(cfg["resblock"]) == "1" and cfg["hidden_channels"] % 64 == 0 and
+            cfg["filter_channels"] % 64 == 0 and cfg["inter_channels"] % 64 == 0 and
+            (cfg["upsample_initial_channel"] >> n_ups) % 64 == 0)
+
+
 def pack(w, cfg, tc=True):
     """w: folded state dict (reference names); returns (blob float32[n], manifest str).
     tc=True also packs split-bf16 copies of the decoder convs for the tcgen05 path (precision mode 1)."""
-    tc = tc and cfg["decoder"] == "mb_istft" and str(cfg["resblock"]) == "1"
+    tc = tc and tc_supported(cfg)
     g = lambda k: w[k].detach().cpu().numpy() if hasattr(w[k], "detach") else np.asarray(w[k])
     H, I, G = cfg["hidden_channels"], cfg["inter_channels"], cfg["gin_channels"]
     D = cfg["dp_filter_channels"]
