@@ -103,6 +103,16 @@ def test_oracle_on_onnx_weights_reproduces_the_reference_output():
     assert np.abs(o["o"][0, 0].numpy() - g["wav"]).max() < 1e-5
 
 
+def test_session_packing_accepts_the_numpy_state_dict():
+    """VitsSession folds + packs whatever Model hands it; for model.onnx that is a dict of numpy arrays."""
+    sd, cfg, _ = _tiny()
+    folded = weights.fold_weight_norm(sd)
+    assert not weights.tc_supported(cfg)
+    blob, man = weights.pack(folded, cfg)
+    b2, m2 = weights.pack(sd, cfg, tc=False)
+    assert man == m2 and np.array_equal(blob, b2)
+
+
 @pytest.mark.gpu
 def test_engine_from_onnx_initializers_reproduces_the_reference_output():
     """The deployment path end to end on the GPU: model.onnx -> initializers -> packed weights -> CUDA engine (fp32 mode:
@@ -124,3 +134,33 @@ def test_engine_from_onnx_initializers_reproduces_the_reference_output():
             assert np.abs(wav[0][: len(g["wav"])] - g["wav"]).max() < 1e-3
     finally:
         e.close()
+
+
+@pytest.mark.gpu
+def test_model_directory_in_deployed_layout_synthesizes(tmp_path):
+    """What a vosk-tts user has on disk -- model.onnx + config.json + dictionary (vosk_tts/model.py:40-55) -- is all that
+    `Model` / `Synth` need: text in, 22.05 kHz 16-bit WAV out, no checkpoint, no training json."""
+    import json
+    import shutil
+    import wave
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from vosk_tts_b200.model import Model
+    from vosk_tts_b200.synth import Synth
+    phones = ["_", "^", "$", " ", ",", ".", "p", "rj", "i0", "i1", "v", "vj", "e0", "e1", "t", "j", "a0", "a1", "m", "mj", "r", "o0", "o1"]
+    cfg = {"phoneme_id_map": {p: [i] for i, p in enumerate(phones)}, "inference": {"noise_level": 0.7, "speech_rate": 1.25},
+           "model_type": "vits", "audio": {"sample_rate": 22050}}
+    (tmp_path / "config.json").write_text(json.dumps(cfg), encoding="utf-8")
+    (tmp_path / "dictionary").write_text("привет 1.0 p rj i0 vj e1 t\n", encoding="utf-8")
+    shutil.copy(TINY, tmp_path / "model.onnx")
+    m = Model(model_path=tmp_path)
+    assert m.onnx.cfg["hidden_channels"] == 64 and m.onnx.cfg["n_speakers"] == 4
+    s = Synth(m)
+    out = tmp_path / "o.wav"
+    s.synth("Привет, мир", str(out), speaker_id=3)
+    with wave.open(str(out)) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate()) == (1, 2, 22050)
+        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
+    assert len(pcm) > 0 and len(pcm) % 256 == 0 and int(m.onnx.last_y_lengths[0]) * 256 == len(pcm)
+    assert pcm.std() > 10

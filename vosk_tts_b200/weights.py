@@ -14,6 +14,7 @@ def fold_weight_norm(sd):
     """w = g * v / ||v||, the norm taken over all dims but 0 (torch.nn.utils.weight_norm dim=0;
     for ConvTranspose1d dim 0 is the *input* channel, e.g. dec.ups.0.weight_g is [512,1,1])."""
     out = {}
+    sd = {k: (torch.from_numpy(np.array(v)) if isinstance(v, np.ndarray) else v) for k, v in sd.items()}   # numpy (model.onnx) or torch
     for k, v in sd.items():
         if k.endswith(".weight_v"):
             base = k[: -len("_v")]
