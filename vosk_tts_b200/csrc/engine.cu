@@ -200,6 +200,9 @@ struct vtts_engine {
   int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
+  cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+  int mrf_branch = 0;                      // VTTS_MRF_BRANCH=1: one stream per resblock chain (measured slower: 1.74 vs 1.62 ms)
   float stage_ms[8] = {};
   bool ev_valid = false;
 
@@ -912,23 +915,51 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
       pj[j] = planes(slot++, rows, ch, zero);
       pt[j] = planes(slot++, rows, ch, zero);
     }
-    for (int d = 0; d < nd; ++d) {
-      std::vector<TcSpec> p1, p2;
-      for (int j = 0; j < nk; ++j) {
-        const RbW& R = rbs[i * nk + j];
-        const int k = c.resblock_kernel_sizes[j], dl = c.resblock_dilations[j][d];
-        TcSpec a;
-        a.in = (d == 0) ? px : pj[j]; a.w = R.t1[d]; a.bias = R.c1[d].b; a.Cin = ch; a.Cout = ch; a.k = k; a.dil = dl;
-        a.pad = dl * (k - 1) / 2; a.out = pt[j]; a.pl_slope = 0.1f;
-        TcSpec b2;
-        b2.in = pt[j]; b2.w = R.t2[d]; b2.bias = R.c2[d].b; b2.Cin = ch; b2.Cout = ch; b2.k = k; b2.dil = 1; b2.pad = (k - 1) / 2;
-        b2.res = (d == 0) ? X : xj[j]; b2.ldr = ch; b2.y = xj[j]; b2.ldy = ch;
-        if (d + 1 < nd) { b2.out = pj[j]; b2.pl_slope = 0.1f; }
-        p1.push_back(a);
-        p2.push_back(b2);
+    auto rb_pair = [&](int j, int d, TcSpec& a, TcSpec& b2) {
+      const RbW& R = rbs[i * nk + j];
+      const int k = c.resblock_kernel_sizes[j], dl = c.resblock_dilations[j][d];
+      a.in = (d == 0) ? px : pj[j]; a.w = R.t1[d]; a.bias = R.c1[d].b; a.Cin = ch; a.Cout = ch; a.k = k; a.dil = dl;
+      a.pad = dl * (k - 1) / 2; a.out = pt[j]; a.pl_slope = 0.1f;
+      b2.in = pt[j]; b2.w = R.t2[d]; b2.bias = R.c2[d].b; b2.Cin = ch; b2.Cout = ch; b2.k = k; b2.dil = 1; b2.pad = (k - 1) / 2;
+      b2.res = (d == 0) ? X : xj[j]; b2.ldr = ch; b2.y = xj[j]; b2.ldy = ch;
+      if (d + 1 < nd) { b2.out = pj[j]; b2.pl_slope = 0.1f; }
+    };
+    // The nk resblocks of the MRF (models.py:1030-1036) are independent chains of 2*nd convs.  Grouped launches keep them
+    // in lock-step, so every step lasts as long as its largest kernel size.  Experiment (VTTS_MRF_BRANCH=1, off): for
+    // single utterances each chain runs on its own stream (fork / join with events, also inside the captured graph) with
+    // the split-K width that suits its own k-loop -- correct, but the concurrent cluster launches of three streams
+    // contend and the step gets slower (1.74 vs 1.62 ms).
+    long group_tiles = 0;
+    for (int b = 0; b < B; ++b) group_tiles += (long)nk * ((h_frm_len[b] * rm + TC_BM - 1) / TC_BM) * ((ch + 63) / 64);
+    const bool branch = mrf_branch && !profiling && nk > 1 && nk - 1 <= 3 && group_tiles <= 148;
+    if (branch) {
+      struct Restore { cudaStream_t& s; cudaStream_t v; ~Restore() { s = v; } } restore{stream, stream};
+      cudaStream_t main_stream = stream;
+      CK(cudaEventRecord(ev_fork, main_stream));
+      for (int j = nk - 1; j >= 0; --j) {              // largest kernel size first
+        if (j > 0) {
+          CK(cudaStreamWaitEvent(side[j - 1], ev_fork, 0));
+          stream = side[j - 1];
+        } else {
+          stream = main_stream;
+        }
+        for (int d = 0; d < nd; ++d) {
+          TcSpec a, b2;
+          rb_pair(j, d, a, b2);
+          launch_tc({a}, rm, fl, fo, maxFrm, B);
+          launch_tc({b2}, rm, fl, fo, maxFrm, B);
+        }
+        if (j > 0) CK(cudaEventRecord(ev_join[j - 1], stream));
       }
-      launch_tc(p1, rm, fl, fo, maxFrm, B);
-      launch_tc(p2, rm, fl, fo, maxFrm, B);
+      stream = main_stream;
+      for (int j = 1; j < nk; ++j) CK(cudaStreamWaitEvent(main_stream, ev_join[j - 1], 0));
+    } else {
+      for (int d = 0; d < nd; ++d) {
+        std::vector<TcSpec> p1(nk), p2(nk);
+        for (int j = 0; j < nk; ++j) rb_pair(j, d, p1[j], p2[j]);
+        launch_tc(p1, rm, fl, fo, maxFrm, B);
+        launch_tc(p2, rm, fl, fo, maxFrm, B);
+      }
     }
     const bool last = (i + 1 == c.n_upsamples);
     Planes nxt = planes(slot++, rows + (last ? B : 0), ch, zero);
@@ -1786,6 +1817,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
                 h->tc_cluster_cap[0][2], h->tc_cluster_cap[1][0], h->tc_cluster_cap[1][1], h->tc_cluster_cap[1][2]);
     }
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& st : h->side) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (auto& e : h->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : h->ev) CK(cudaEventCreate(&e));
     h->blob_floats = blob_floats;
     CK(cudaMalloc(&h->d_blob, blob_floats * sizeof(float)));
@@ -1806,6 +1840,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
+    if (const char* e = getenv("VTTS_MRF_BRANCH")) h->mrf_branch = atoi(e);
     if (const char* e = getenv("VTTS_ATTN_SPLIT")) h->attn_split = atoi(e);       // 0: never use the split-KV attention
     if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
@@ -1860,6 +1895,9 @@ void vtts_destroy(vtts_handle h) {
   for (auto& e : h->prof_ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->tc_prof_ev) if (e) cudaEventDestroy(e);
   for (auto& b : h->pl_pool) fr(b.p);
+  for (auto& st : h->side) if (st) cudaStreamDestroy(st);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (auto& e : h->ev_join) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
