@@ -164,3 +164,24 @@ def test_model_directory_in_deployed_layout_synthesizes(tmp_path):
         pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
     assert len(pcm) > 0 and len(pcm) % 256 == 0 and int(m.onnx.last_y_lengths[0]) * 256 == len(pcm)
     assert pcm.std() > 10
+
+
+def test_reader_rejects_external_data(tmp_path):
+    """A TensorProto with data_location = EXTERNAL (field 14 = 1) cannot be served from the file alone: loud error."""
+    def varint(n):
+        out = b""
+        while True:
+            b7 = n & 0x7F
+            n >>= 7
+            out += bytes([b7 | (0x80 if n else 0)])
+            if not n:
+                return out
+    def field(no, wt, payload):
+        return varint((no << 3) | wt) + (varint(len(payload)) + payload if wt == 2 else payload)
+    tensor = field(1, 0, varint(4)) + field(2, 0, varint(1)) + field(8, 2, b"w") + field(14, 0, varint(1))
+    graph = field(5, 2, tensor)
+    model = field(7, 2, graph)
+    p = tmp_path / "ext.onnx"
+    p.write_bytes(model)
+    with pytest.raises(ValueError, match="external data"):
+        ow.read_graph(str(p))
