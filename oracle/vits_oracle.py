@@ -376,13 +376,18 @@ def decoder_trunk(z, w, cfg, g=None):
 
 
 def decoder_mb_istft(z, w, cfg):
-    """models.py:1016-1054 with OnnxSTFT (is_onnx=True) and PQMF.synthesis (pqmf.py:105-116)."""
-    sb = cfg["subbands"]
+    """The three inverse-STFT decoders, all with OnnxSTFT (is_onnx=True):
+    mb_istft  Multiband_iSTFT_Generator.forward models.py:1016-1054 + PQMF.synthesis pqmf.py:105-116;
+    ms_istft  Multistream_iSTFT_Generator.forward models.py:1117-1158: same, conv_post has a bias and the fixed PQMF
+              synthesis bank is replaced by the learned 63-tap ``multistream_conv_post`` (zero padding 31, no bias);
+    istft     iSTFT_Generator.forward models.py:947-965: one band, ``conv_post``, no filter bank."""
+    kind = cfg["decoder"]
+    sb = 1 if kind == "istft" else cfg["subbands"]
     nfft, hop = cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]
     x = decoder_trunk(z, w, cfg)
     x = F.leaky_relu(x)                                   # default slope 0.01 (:1038)
     x = F.pad(x, (1, 0), mode="reflect")
-    x = conv(x, w, "dec.subband_conv_post", padding=3)
+    x = conv(x, w, "dec.conv_post" if kind == "istft" else "dec.subband_conv_post", padding=3)
     B, _, L = x.shape
     x = x.reshape(B, sb, x.shape[1] // sb, L)
     nb = nfft // 2 + 1
@@ -394,10 +399,15 @@ def decoder_mb_istft(z, w, cfg):
     y = y[:, :, nfft // 2:]
     y = y[:, :, :-(nfft // 2)]
     y_mb = y.reshape(B, sb, y.shape[-1])
+    if kind == "istft":
+        return y_mb, None
     updown = torch.zeros(sb, sb, sb)
     for k in range(sb):
         updown[k, k, 0] = 1.0
     up = F.conv_transpose1d(y_mb, updown * sb, stride=sb)
+    if kind == "ms_istft":
+        wav = F.conv1d(up, w["dec.multistream_conv_post.weight"], None, padding=31)      # get_padding(63, 1) = 31
+        return wav, up                                    # the reference returns the zero-stuffed bands as y_mb_hat
     wav = F.conv1d(F.pad(up, (31, 31)), pqmf_synthesis_filter(sb))
     return wav, y_mb
 
@@ -437,7 +447,7 @@ def infer(w, cfg, tokens, lengths, sid, scales, eps_dp, eps_z=None, return_all=F
     z_p = m_e + e * torch.exp(logs_e) * noise_scale
     z = flow_reverse(z_p, y_mask, g, w, cfg)
     zin = z * y_mask
-    if cfg["decoder"] == "mb_istft":
+    if cfg["decoder"] in ("mb_istft", "ms_istft", "istft"):
         o, o_mb = decoder_mb_istft(zin, w, cfg)
     else:
         o, o_mb = decoder_hifigan(zin, w, cfg, g)

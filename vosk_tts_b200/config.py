@@ -33,7 +33,8 @@ DEFAULT_CONFIG = {
     "dp_n_flows": 4,
     "dp_num_bins": 10,
     "dp_tail_bound": 5.0,
-    "decoder": "mb_istft",           # "mb_istft" (Multiband_iSTFT_Generator) | "hifigan" (Generator)
+    "decoder": "mb_istft",           # "mb_istft" (Multiband_iSTFT_Generator) | "ms_istft" (Multistream_iSTFT_Generator) |
+                                     # "istft" (iSTFT_Generator) | "hifigan" (Generator)
     "resblock": "1",
     "resblock_kernel_sizes": [3, 7, 11],
     "resblock_dilation_sizes": [[1, 3, 5], [1, 3, 5], [1, 3, 5]],
@@ -45,6 +46,9 @@ DEFAULT_CONFIG = {
     "gen_istft_hop_size": 4,
     "sampling_rate": 22050,
 }
+
+
+ISTFT_DECODERS = ("mb_istft", "ms_istft", "istft")      # decoders that end in conv_post -> exp / pi*sin -> inverse STFT
 
 
 def from_training_json(path_or_dict, n_vocab=62):
@@ -67,10 +71,14 @@ def from_training_json(path_or_dict, n_vocab=62):
     out["use_spk_conditioned_encoder"] = bool(m.get("use_spk_conditioned_encoder", False))
     out["use_transformer_flows"] = bool(m.get("use_transformer_flows", False))
     out["transformer_flow_type"] = m.get("transformer_flow_type", "pre_conv2")
+    # same precedence as SynthesizerTrn.__init__ (models.py:1585-1606)
     if m.get("mb_istft_vits", False):
         out["decoder"] = "mb_istft"
-    elif m.get("ms_istft_vits", False) or m.get("istft_vits", False):
-        raise ValueError("decoder variant not supported by this engine (only mb_istft / hifigan)")
+    elif m.get("ms_istft_vits", False):
+        out["decoder"] = "ms_istft"
+    elif m.get("istft_vits", False):
+        out["decoder"] = "istft"
+        out["subbands"] = 1                     # iSTFT_Generator has a single band and no synthesis filter bank
     else:
         out["decoder"] = "hifigan"
     if out["use_transformer_flows"] and out["transformer_flow_type"] != "pre_conv2":
@@ -83,6 +91,6 @@ def hop_total(cfg):
     up = 1
     for u in cfg["upsample_rates"]:
         up *= u
-    if cfg["decoder"] == "mb_istft":
+    if cfg["decoder"] in ISTFT_DECODERS:
         up *= cfg["gen_istft_hop_size"] * cfg["subbands"]
     return up

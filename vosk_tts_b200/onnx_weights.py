@@ -216,7 +216,17 @@ def config_from_onnx(path, sampling_rate=22050):
     cfg["use_transformer_flows"] = any(k.startswith("flow.flows.0.pre_transformer.") for k in sd)
     cfg["transformer_flow_type"] = "pre_conv2"
     # decoder
-    cfg["decoder"] = "mb_istft" if "dec.subband_conv_post.weight" in sd else "hifigan"
+    # OnnxSTFT's inverse basis [n_fft+2, 1, n_fft] (stft.py:191-214): an anonymous constant or the buffer ``dec.stft.inverse_basis``
+    basis = [(k, v) for k, v in inits.items() if (k.startswith("onnx::ConvTranspose") or k.endswith("inverse_basis"))
+             and v.ndim == 3 and v.shape[1] == 1 and v.shape[0] == v.shape[2] + 2 and k in attr_of]
+    if "dec.multistream_conv_post.weight" in sd:
+        cfg["decoder"] = "ms_istft"
+    elif "dec.subband_conv_post.weight" in sd:
+        cfg["decoder"] = "mb_istft"
+    elif basis and "dec.conv_post.weight" in sd:
+        cfg["decoder"] = "istft"
+    else:
+        cfg["decoder"] = "hifigan"
     cfg["upsample_initial_channel"] = int(sd["dec.conv_pre.weight"].shape[0])
     n_ups = _count(sd, r"dec\.ups\.(\d+)\.weight")
     cfg["upsample_kernel_sizes"] = [int(sd["dec.ups.%d.weight" % i].shape[2]) for i in range(n_ups)]
@@ -232,14 +242,14 @@ def config_from_onnx(path, sampling_rate=22050):
         n_conv = _count(sd, r"dec\.resblocks\.%d\.%s\.(\d+)\.weight" % (j, stem))
         dil.append([int((attr_of["dec.resblocks.%d.%s.%d.weight" % (j, stem, m)][1].get("dilations") or [1])[0]) for m in range(n_conv)])
     cfg["resblock_dilation_sizes"] = dil
-    if cfg["decoder"] == "mb_istft":
-        basis = [(k, v) for k, v in inits.items() if k.startswith("onnx::ConvTranspose") and v.ndim == 3 and v.shape[1] == 1]
+    if cfg["decoder"] != "hifigan":
         if len(basis) != 1:
-            raise ValueError("cannot locate the inverse-STFT basis of the multi-band decoder in the graph")
+            raise ValueError("cannot locate the inverse-STFT basis of the decoder in the graph")
         n_fft = int(basis[0][1].shape[2])
         cfg["gen_istft_n_fft"] = n_fft
         cfg["gen_istft_hop_size"] = int(attr_of[basis[0][0]][1]["strides"][0])
-        cfg["subbands"] = int(sd["dec.subband_conv_post.weight"].shape[0]) // (n_fft + 2)
+        post = "dec.conv_post.weight" if cfg["decoder"] == "istft" else "dec.subband_conv_post.weight"
+        cfg["subbands"] = int(sd[post].shape[0]) // (n_fft + 2)
     if not cfg["use_transformer_flows"]:
         raise ValueError("plain coupling flows are unreachable through the reference exporter; unexpected graph")
     return cfg

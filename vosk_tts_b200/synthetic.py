@@ -114,7 +114,7 @@ def _spec(cfg):
 
     # --- decoder (models.py:974-1063 / 845-898, modules.py:187-258)
     C0 = cfg["upsample_initial_channel"]
-    if cfg["decoder"] == "mb_istft":
+    if cfg["decoder"] in ("mb_istft", "ms_istft", "istft"):
         conv("dec.conv_pre", C0, I, 7, wn=True, gain=1.0)
     else:      # plain Generator: conv_pre is not weight-normed and a speaker projection is added to its output (models.py:851,869-875)
         conv("dec.conv_pre", C0, I, 7, wn=False, gain=1.0)
@@ -136,6 +136,11 @@ def _spec(cfg):
     if cfg["decoder"] == "mb_istft":
         conv("dec.subband_conv_post", cfg["subbands"] * (cfg["gen_istft_n_fft"] + 2), ch, 7,
              wn=True, bias=False, gain=0.25)
+    elif cfg["decoder"] == "ms_istft":      # models.py:1095 (bias!), :1107 learned 63-tap merge filter
+        conv("dec.subband_conv_post", cfg["subbands"] * (cfg["gen_istft_n_fft"] + 2), ch, 7, wn=True, bias=True, gain=0.25)
+        conv("dec.multistream_conv_post", 1, cfg["subbands"], 63, wn=True, bias=False, gain=1.0)
+    elif cfg["decoder"] == "istft":         # models.py:928
+        conv("dec.conv_post", cfg["gen_istft_n_fft"] + 2, ch, 7, wn=True, bias=False, gain=0.25)
     else:
         conv("dec.conv_post", 1, ch, 7, wn=False, bias=False, gain=0.5)     # plain Conv1d (models.py:868)
     return out

@@ -161,7 +161,7 @@ def convt_phases(u, K):
 def tc_supported(cfg):
     """The tcgen05 conv path packs 64-channel K chunks: every conv it takes over must have Cin % 64 == 0."""
     n_ups = len(cfg["upsample_rates"])
-    return (cfg["decoder"] == "mb_istft" and str(cfg["resblock"]) == "1" and cfg["hidden_channels"] % 64 == 0 and
+    return (cfg["decoder"] in ("mb_istft", "ms_istft", "istft") and str(cfg["resblock"]) == "1" and cfg["hidden_channels"] % 64 == 0 and
             cfg["filter_channels"] % 64 == 0 and cfg["inter_channels"] % 64 == 0 and
             (cfg["upsample_initial_channel"] >> n_ups) % 64 == 0)
 
@@ -225,7 +225,7 @@ def pack(w, cfg, tc=True):
             for i in range(nl):
                 rows_w.append(cw[i * 2 * H:(i + 1) * 2 * H][il])
                 rows_b.append(cb[i * 2 * H:(i + 1) * 2 * H][il])
-        if cfg["decoder"] != "mb_istft" and "dec.cond.weight" in w:
+        if cfg["decoder"] == "hifigan" and "dec.cond.weight" in w:
             rows_w.append(g("dec.cond.weight")[:, :, 0])       # Generator's speaker projection (models.py:869-875)
             rows_b.append(g("dec.cond.bias"))
         P.add("cond.w", np.concatenate(rows_w, 0))
@@ -312,12 +312,25 @@ def pack(w, cfg, tc=True):
                         P.conv_tc("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)))
                 else:
                     P.conv("dec.rb%d.c.%d" % (n, d), g("dec.resblocks.%d.convs.%d.weight" % (n, d)), g("dec.resblocks.%d.convs.%d.bias" % (n, d)))
-    if cfg["decoder"] == "mb_istft":
-        P.conv("dec.post", g("dec.subband_conv_post.weight"), None)
+    if cfg["decoder"] in ("mb_istft", "ms_istft", "istft"):
+        # All three end in conv_post -> exp / pi*sin -> inverse STFT -> zero-stuffing by `subbands` -> a 63-tap filter per band
+        # (zero padding 31).  Only the filter differs: the fixed PQMF synthesis bank (pqmf.py:63-89), the learned
+        # multistream_conv_post (models.py:1107), or -- one band, nothing after the iSTFT (models.py:962-965) -- a unit impulse.
+        post = "dec.conv_post" if cfg["decoder"] == "istft" else "dec.subband_conv_post"
+        post_b = g(post + ".bias") if (post + ".bias") in w else None          # only the multistream decoder has one (:1095)
+        P.conv("dec.post", g(post + ".weight"), post_b)
         if tc:
-            P.conv_tc("dec.post", g("dec.subband_conv_post.weight"))
+            P.conv_tc("dec.post", g(post + ".weight"))
         P.add("dec.istft", istft_inverse_basis(cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]))
-        P.add("dec.pqmf", pqmf_synthesis_filter(cfg["subbands"]))
+        if cfg["decoder"] == "mb_istft":
+            bank = pqmf_synthesis_filter(cfg["subbands"])
+        elif cfg["decoder"] == "ms_istft":
+            bank = g("dec.multistream_conv_post.weight")[0]
+            assert bank.shape == (cfg["subbands"], 63), bank.shape
+        else:
+            bank = np.zeros((1, 63), np.float32)
+            bank[0, 31] = 1.0
+        P.add("dec.pqmf", bank)
     else:
         P.conv("dec.post", g("dec.conv_post.weight"), None)
     return P.finish()
