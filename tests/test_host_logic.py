@@ -132,3 +132,25 @@ def test_session_rejects_non_vits_feeds():
     with pytest.raises(ValueError):
         VitsSession.run(s, None, {"input": np.zeros((1, 5, 4), np.int64), "input_lengths": [4], "scales": [0, 1, 0],
                                    "sid": [0], "bert": None, "phone_duration_extra": None})
+
+
+def test_training_json_selects_the_decoder_like_the_reference():
+    """SynthesizerTrn.__init__ picks the decoder by flag precedence mb > ms > istft > plain (models.py:1585-1606)."""
+    from vosk_tts_b200 import config as C
+    base = {"data": {"n_speakers": 3, "sampling_rate": 22050},
+            "model": {"inter_channels": 64, "hidden_channels": 64, "filter_channels": 128, "n_heads": 2, "n_layers": 3,
+                      "kernel_size": 3, "resblock": "1", "resblock_kernel_sizes": [3], "resblock_dilation_sizes": [[1, 3, 5]],
+                      "upsample_rates": [4, 4], "upsample_initial_channel": 64, "upsample_kernel_sizes": [16, 16],
+                      "subbands": 4, "gen_istft_n_fft": 16, "gen_istft_hop_size": 4, "gin_channels": 32,
+                      "use_transformer_flows": True, "transformer_flow_type": "pre_conv2"}}
+    import copy
+    def cfg(**flags):
+        j = copy.deepcopy(base)
+        j["model"].update(flags)
+        return C.from_training_json(j, n_vocab=10)
+    assert cfg(mb_istft_vits=True, ms_istft_vits=True)["decoder"] == "mb_istft"
+    assert cfg(ms_istft_vits=True, istft_vits=True)["decoder"] == "ms_istft"
+    c = cfg(istft_vits=True)
+    assert c["decoder"] == "istft" and c["subbands"] == 1 and C.hop_total(c) == 4 * 4 * 4
+    assert cfg()["decoder"] == "hifigan" and C.hop_total(cfg()) == 16
+    assert C.hop_total(cfg(mb_istft_vits=True)) == 256
