@@ -1,4 +1,5 @@
-"""Stage-by-stage comparison of the CUDA engine against the oracle on the golden cases (GPU box)."""
+"""TEST INFRASTRUCTURE (not collected by pytest): stage-by-stage comparison of the CUDA engine against the oracle on the
+golden cases, for debugging on the GPU box:  python tests/gpu_debug.py t128_sid2 t17_sid2"""
 import os, sys, time
 import numpy as np, torch
 import torch.nn.functional as F
