@@ -60,7 +60,9 @@ typedef struct vtts_config {
   int32_t upsample_kernel_sizes[8];
   int32_t upsample_initial_channel;
   int32_t subbands, istft_n_fft, istft_hop;
-  int32_t precision;               /* 0 = fp32 FFMA everywhere; 1 = split-bf16 tcgen05 for dense convs */
+  int32_t precision;               /* 0 = fp32 FFMA everywhere; 1 = split-bf16 tcgen05 for the flow + decoder (dense convs and
+                                      attention); 2 = text encoder on tcgen05 as well */
+  int32_t flow_n_heads;            /* heads of the flow's pre_transformer: the reference hard-codes 2 (models.py:355) */
 } vtts_config;
 
 /* Replaces onnxruntime.InferenceSession(model.onnx) (vosk_tts/model.py:46).
@@ -157,6 +159,11 @@ int vtts_timeline(vtts_handle h, int enable, unsigned long long* out, size_t max
  * host memory in the engine's channels-last packed layout. */
 int vtts_debug_flags(vtts_handle h, int flags);
 int vtts_debug_read(vtts_handle h, const char* name, float* out, size_t max_floats, size_t* n_out);
+/* Unit-test hook for the relative-position attention kernels (attentions.py:165-196): one launch of layer "enc.<i>" or
+ * "flow.<f>.tr" on a host fp32 qkv tensor [T][3H] of one utterance; out receives fp32 [T][H].  use_tc = 1 selects the
+ * tcgen05 kernel (attn_tc.cuh), 0 the fp32 FFMA kernels.  iters > 0: *ms_out = average device time of `iters` more launches. */
+int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host, int T, int use_tc, float* out_host, int iters,
+                         float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -9,6 +9,7 @@ and the two RNG draws (models.py:96, :1700) replaced by seeded tensors that are 
 fixture.  Weights are NOT stored (127 MB); they are regenerated from the seed, and a float64
 checksum of the regenerated tensors is stored to detect generator drift.
 """
+import json
 import os
 import sys
 
@@ -32,6 +33,15 @@ CASES = [
     ("t33_nonoise", [33], [0], [0.0, 1.0, 0.0], 33),
     ("ragged3", [9, 40, 23], [1, 2, 199], [0.8, 1.0, 0.8], 3),
     ("t1_single", [1], [5], [0.8, 1.0, 0.8], 1),
+]
+
+
+# Architecture variants: (fixture name, overrides of the training json's "model" block, T_x, sid, scales, input seed).
+# "plainflow": use_transformer_flows=False with a transformer_flow_type other than the "mono_layer_post_residual" default
+# selects the final else-branch of ResidualCouplingTransformersBlock.__init__ (models.py:735-747): plain
+# modules.ResidualCouplingLayer + Flip, i.e. exactly ResidualCouplingBlock (models.py:765-810).
+VARIANTS = [
+    ("plainflow_t40", {"use_transformer_flows": False, "transformer_flow_type": "pre_conv2"}, 40, 3, [0.8, 1.1, 0.8], 40),
 ]
 
 
@@ -74,6 +84,29 @@ def main():
             print(name, u, "T_x", T, "T_y", Ty, "wav absmax %.3f" % float(r["o"].abs().max()))
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print("weights checksum", weight_checksum(sd))
+    import copy
+    for name, over, T, sid, scales, seed in VARIANTS:
+        jc = copy.deepcopy(rh.load_ref_config())
+        jc["model"].update(over)
+        vcfg = C.from_training_json(jc)
+        vsd = synthetic.make_random_checkpoint(vcfg, WEIGHT_SEED)
+        vnet = rh.build_reference_model(vsd, cfg=jc)
+        g = torch.Generator().manual_seed(seed)
+        tok = torch.randint(0, vcfg["n_vocab"], (1, T), generator=g)
+        eps_dp = torch.randn(1, 2, T, generator=g)
+        eps_z_full = torch.randn(1, vcfg["inter_channels"], 24 * T + 8, generator=g)
+        r = rh.reference_infer(vnet, tok, torch.tensor([T]), torch.tensor([sid]), scales, eps_dp, lambda s: eps_z_full[:, :, :s[2]])
+        Ty = r["o"].shape[-1] // 256
+        attn = r["attn"][0, 0]
+        out = {"weight_seed": WEIGHT_SEED, "weight_checksum": weight_checksum(vsd), "scales": np.asarray(scales, np.float32), "n": 1,
+               "model_overrides": np.asarray(json.dumps(over)),
+               "u0_tokens": tok[0].numpy().astype(np.int64), "u0_sid": np.int64(sid), "u0_eps_dp": eps_dp[0].numpy(),
+               "u0_eps_z": eps_z_full[0, :, :Ty].numpy().copy(), "u0_w_ceil": attn.sum(0).numpy().astype(np.int32),
+               "u0_idx": attn.argmax(1).numpy().astype(np.int32), "u0_y_length": np.int64(Ty), "u0_wav": r["o"][0, 0].numpy(),
+               "u0_z_p": r["z_p"][0].numpy(), "u0_z": r["z"][0].numpy(), "u0_o_mb": r["o_mb"][0].numpy()}
+        print(name, "T_x", T, "T_y", Ty, "wav absmax %.3f" % float(r["o"].abs().max()),
+              "|z - z_p| max %.3f (the flow must not be an identity)" % float((r["z"] - r["z_p"]).abs().max()))
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
 
 
 if __name__ == "__main__":

@@ -96,7 +96,15 @@ def build_reference_model(state_dict=None, cfg=None, n_vocab=62, quiet=True):
             assert not unexpected, unexpected
         net.eval()
         net.dec.remove_weight_norm()
-        net.flow.remove_weight_norm()
+        try:
+            net.flow.remove_weight_norm()
+        except AttributeError:
+            # use_transformer_flows=False: the block holds plain modules.ResidualCouplingLayer (models.py:747-757 ->
+            # modules.py:298-343), which has no remove_weight_norm of its own -- the reference exporter would fail here
+            # (onnx_export.py:79).  Fold the same tensors through the WN module's own method (modules.py:178-184).
+            for i, l in enumerate(net.flow.flows):
+                if i % 2 == 0:
+                    l.enc.remove_weight_norm()
     return net
 
 

@@ -262,3 +262,33 @@ def test_session_run_matches_reference_call_shape(packed, cfg):
     assert out.dtype == np.float32 and out.ndim == 4 and out.shape[:3] == (1, 1, 1)
     assert out.shape[3] == int(s.last_y_lengths[0]) * 256
     s.close()
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_plain_coupling_flow_variant_vs_reference_fixture(precision):
+    """use_transformer_flows=False (plain ResidualCouplingLayer + Flip == ResidualCouplingBlock, models.py:765-810,
+    vc/modules.py:300-345) against the fixture the unmodified reference produced with that flag."""
+    import copy
+    import json
+    from vosk_tts_b200 import config as C, synthetic, weights
+    from vosk_tts_b200.engine import Engine
+    g = load_golden("plainflow_t40")
+    cfg = copy.deepcopy(C.DEFAULT_CONFIG)
+    cfg.update(json.loads(str(g["model_overrides"])))
+    w = weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, int(g["weight_seed"])))
+    blob, man = weights.pack(w, cfg)
+    eng = Engine(cfg, blob, man, device=0, precision=precision)
+    try:
+        c = _case(g, 0)
+        T = len(c["tok"])
+        eng.debug_flags(1)
+        ylen, dur = eng.durations(c["tok"][None], [T], [c["sid"]], g["scales"], c["eps_dp"][None], want_durations=True)
+        assert int(ylen[0]) == c["Ty"]
+        assert np.array_equal(dur[0], c["w_ceil"])
+        wav, idx = eng.synthesize(ylen, c["eps_z"][None], want_alignment=True)
+        assert np.array_equal(idx[0, : c["Ty"]], c["idx"])
+        z = eng.debug_read("z").reshape(c["Ty"], -1)
+        assert np.abs(z - c["z"].T).max() < 3e-4
+        assert np.abs(wav[0, : c["Ty"] * 256] - c["wav"]).max() < WAV_TIGHT
+    finally:
+        eng.close()

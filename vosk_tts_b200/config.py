@@ -24,6 +24,7 @@ DEFAULT_CONFIG = {
     "cond_layer_idx": 2,
     "use_transformer_flows": True,
     "transformer_flow_type": "pre_conv2",
+    "flow_n_heads": 2,               # heads of the flow's pre_transformer: hard-coded in the reference (models.py:355), NOT n_heads
     "flow_kernel_size": 5,
     "flow_dilation_rate": 1,
     "flow_wn_layers": 4,
@@ -70,7 +71,22 @@ def from_training_json(path_or_dict, n_vocab=62):
             out[k] = m[k]
     out["use_spk_conditioned_encoder"] = bool(m.get("use_spk_conditioned_encoder", False))
     out["use_transformer_flows"] = bool(m.get("use_transformer_flows", False))
-    out["transformer_flow_type"] = m.get("transformer_flow_type", "pre_conv2")
+    # reference defaults (models.py:1561-1564): note the flow type defaults to "mono_layer_post_residual"
+    out["transformer_flow_type"] = m.get("transformer_flow_type", "mono_layer_post_residual")
+    # Only what the engine implements is accepted, with the reason up front instead of a KeyError inside pack():
+    #  * use_sdp=False builds the deterministic DurationPredictor (models.py:1625-1628): not implemented;
+    #  * use_transformer_flows=True needs "pre_conv2" (ResidualCouplingTransformersLayer2, models.py:329-396);
+    #  * use_transformer_flows=False is the plain ResidualCouplingLayer + Flip stack ONLY when the flow type is not
+    #    "mono_layer_post_residual": with that (default!) type the reference appends a MonoTransformerFlowLayer to
+    #    every flow (models.py:716-734), which the engine does not have.
+    if not bool(m.get("use_sdp", True)):
+        raise ValueError("use_sdp=false (deterministic DurationPredictor, models.py:1627) is not supported by this engine")
+    if out["use_transformer_flows"]:
+        if out["transformer_flow_type"] != "pre_conv2":
+            raise ValueError("transformer_flow_type %r not supported (only 'pre_conv2')" % out["transformer_flow_type"])
+    elif out["transformer_flow_type"] == "mono_layer_post_residual":
+        raise ValueError("use_transformer_flows=false with transformer_flow_type 'mono_layer_post_residual' (the reference "
+                         "default) adds MonoTransformerFlowLayers to the flow (models.py:716-734): not supported")
     # same precedence as SynthesizerTrn.__init__ (models.py:1585-1606)
     if m.get("mb_istft_vits", False):
         out["decoder"] = "mb_istft"
@@ -81,8 +97,6 @@ def from_training_json(path_or_dict, n_vocab=62):
         out["subbands"] = 1                     # iSTFT_Generator has a single band and no synthesis filter bank
     else:
         out["decoder"] = "hifigan"
-    if out["use_transformer_flows"] and out["transformer_flow_type"] != "pre_conv2":
-        raise ValueError("transformer_flow_type %r not supported" % out["transformer_flow_type"])
     return out
 
 

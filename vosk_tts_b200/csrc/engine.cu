@@ -19,6 +19,7 @@
 #include "../../include/vtts.h"
 #include "kernels.cuh"
 #include "conv_tc.cuh"
+#include "attn_tc.cuh"
 
 using namespace vtts;
 
@@ -68,6 +69,9 @@ struct EncLayerW {
   LnW ln1, ln2;
   const float* relk = nullptr;
   const float* relv = nullptr;
+  int heads = 1;
+  // split-bf16 [16][128] tiles of the relative-position tables for the tcgen05 attention (null: FFMA attention only)
+  const __nv_bfloat16 *rk_hi = nullptr, *rk_lo = nullptr, *rv_hi = nullptr, *rv_lo = nullptr;
 };
 struct DdsW {
   const float *sep_w, *sep_b;
@@ -202,6 +206,7 @@ struct vtts_engine {
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
+  bool attn_tc = true;                     // tcgen05 attention wherever the qkv conv runs on tensor cores (VTTS_ATTN_TC=0: FFMA attention)
   int mrf_branch = 0;                      // VTTS_MRF_BRANCH=1: one stream per resblock chain (measured slower: 1.74 vs 1.62 ms)
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -327,9 +332,10 @@ struct vtts_engine {
     return c;
   }
   LnW ln(const std::string& name, int C) { return LnW{vec(name + ".g", C), vec(name + ".b", C)}; }
-  EncLayerW enc_layer(const std::string& p, int Hc, int Fc, int ks) {
+  EncLayerW enc_layer(const std::string& p, int Hc, int Fc, int ks, int heads) {
     EncLayerW L;
-    const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
+    L.heads = heads;
+    const int dk = Hc / heads, nrel = 2 * cfg.window_size + 1;
     L.qkv = conv(p + ".qkv", Hc, 3 * Hc, 1);
     L.o = conv(p + ".o", Hc, Hc, 1);
     L.relk = vec(p + ".relk", (size_t)nrel * dk);
@@ -350,6 +356,13 @@ struct vtts_engine {
     return d;
   }
 
+  void bind_rel_tc(EncLayerW& L, const std::string& p) {
+    if (!tensors.count(p + ".rkh")) return;       // (blob packed without the tables: the FFMA attention is used)
+    L.rk_hi = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rkh", 16 * 128 / 2));
+    L.rk_lo = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rkl", 16 * 128 / 2));
+    L.rv_hi = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rvh", 16 * 128 / 2));
+    L.rv_lo = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rvl", 16 * 128 / 2));
+  }
   TcW tcw(const std::string& name, int Cin, int Cout, int k) {
     TcW t;
     const size_t n = (size_t)k * Cout * Cin / 2;
@@ -363,8 +376,13 @@ struct vtts_engine {
     p.C = C; p.rows = rows;
     const size_t n = (size_t)rows * C + 64;
     REQUIRE(slot >= 0 && 2 * slot + 1 < 128, VTTS_ERR_INVALID, "plane slot out of range");
+    const size_t cap_hi = pl_pool[2 * slot].cap, cap_lo = pl_pool[2 * slot + 1].cap;
     p.hi = ensure(pl_pool[2 * slot], n);
     p.lo = ensure(pl_pool[2 * slot + 1], n);
+    // fresh device memory may hold NaN bit patterns: rows a kernel never writes (beyond an utterance's end inside the last
+    // tile) are multiplied by exact zeros in the attention's P V product, so they must at least be finite
+    if (pl_pool[2 * slot].cap != cap_hi) CK(cudaMemsetAsync(p.hi, 0, pl_pool[2 * slot].cap * sizeof(__nv_bfloat16), stream));
+    if (pl_pool[2 * slot + 1].cap != cap_lo) CK(cudaMemsetAsync(p.lo, 0, pl_pool[2 * slot + 1].cap * sizeof(__nv_bfloat16), stream));
     if (zero) {     // gap rows between packed utterances must read as zero through TMA
       CK(cudaMemsetAsync(p.hi, 0, n * sizeof(__nv_bfloat16), stream));
       CK(cudaMemsetAsync(p.lo, 0, n * sizeof(__nv_bfloat16), stream));
@@ -372,6 +390,8 @@ struct vtts_engine {
     return p;
   }
   CUtensorMap make_map(const void* base, int C, long rows, int box_rows);
+  bool attn_tc_ok(const EncLayerW& L, int Hc) const;
+  void launch_attn_tc(const Planes& qkv, float* ao, Planes* pl, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen);
   void launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   void decoder_tc(float* z, const int* fl, const int* fo);
   void flow_tc(float* z, const int* fl, const int* fo);
@@ -444,6 +464,9 @@ void vtts_engine::bind_weights() {
   const int H = c.hidden_channels, I = c.inter_channels, G = c.gin_channels, D = c.dp_filter_channels;
   REQUIRE(H % 32 == 0 && H <= 256 && D % 32 == 0 && D <= 256, VTTS_ERR_INVALID, "hidden/dp channels must be multiples of 32, <= 256");
   REQUIRE((H / c.n_heads) % 32 == 0 && H / c.n_heads <= 128, VTTS_ERR_INVALID, "head dim must be 32/64/96/128");
+  const int fheads = c.flow_n_heads > 0 ? c.flow_n_heads : 2;      // models.py:355: the flow's pre_transformer always has 2 heads
+  REQUIRE(!c.use_transformer_flows || ((H / fheads) % 32 == 0 && H / fheads <= 128 && H % fheads == 0), VTTS_ERR_INVALID,
+          "flow head dim must be 32/64/96/128");
   REQUIRE(c.dp_num_bins <= SPL_MAXB, VTTS_ERR_INVALID, "too many spline bins");
   REQUIRE(c.dp_kernel_size % 2 == 1 && c.flow_kernel_size % 2 == 1, VTTS_ERR_INVALID, "odd kernels expected");
   REQUIRE(c.n_resblock_kernels <= CV_MAXP, VTTS_ERR_INVALID, "at most 4 resblocks per stage");
@@ -464,7 +487,7 @@ void vtts_engine::bind_weights() {
   }
   enc_emb = vec("enc.emb", (size_t)c.n_vocab * H);
   enc.clear();
-  for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size));
+  for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size, c.n_heads));
   enc_proj = conv("enc.proj", H, 2 * I, 1);
   enc_on_tc = c.precision == 2 && H % TC_BK == 0 && c.filter_channels % TC_BK == 0;
   if (enc_on_tc) {
@@ -474,6 +497,7 @@ void vtts_engine::bind_weights() {
       enc[i].t_o = tcw(p + ".o", H, H, 1);
       enc[i].t_ffn1 = tcw(p + ".ffn1", H, c.filter_channels, c.kernel_size);
       enc[i].t_ffn2 = tcw(p + ".ffn2", c.filter_channels, H, c.kernel_size);
+      bind_rel_tc(enc[i], p);
     }
     tc_encproj = tcw("enc.proj", H, 2 * I, 1);
   }
@@ -496,7 +520,7 @@ void vtts_engine::bind_weights() {
     FlowW F;
     const std::string p = "flow." + std::to_string(f);
     F.pre = conv(p + ".pre", I / 2, H, 1);
-    if (c.use_transformer_flows) F.tr = enc_layer(p + ".tr", H, H, c.flow_kernel_size);
+    if (c.use_transformer_flows) F.tr = enc_layer(p + ".tr", H, H, c.flow_kernel_size, fheads);
     for (int i = 0; i < nl; ++i) {
       F.in.push_back(conv(p + ".in" + std::to_string(i), H, 2 * H, c.flow_kernel_size));
       if (i < nl - 1) F.rsx.push_back(conv(p + ".rsx" + std::to_string(i), H, H, 1));
@@ -510,6 +534,7 @@ void vtts_engine::bind_weights() {
         F.t_o = tcw(p + ".tr.o", H, H, 1);
         F.t_ffn1 = tcw(p + ".tr.ffn1", H, H, fk);
         F.t_ffn2 = tcw(p + ".tr.ffn2", H, H, fk);
+        bind_rel_tc(F.tr, p + ".tr");
       }
       for (int i = 0; i < nl; ++i) {
         F.t_in.push_back(tcw(p + ".in" + std::to_string(i), H, 2 * H, fk));
@@ -742,24 +767,59 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   ++launches;
 }
 
+// Attention on the tensor cores (attn_tc.cuh): q, k, v come as the split-bf16 planes the qkv conv's epilogue wrote.
+bool vtts_engine::attn_tc_ok(const EncLayerW& L, int Hc) const {
+  const int dk = Hc / L.heads;
+  return attn_tc && L.rk_hi != nullptr && dk % 32 == 0 && dk <= 128 && 2 * cfg.window_size + 1 <= ATC_RS && (3 * Hc) % 8 == 0;
+}
+void vtts_engine::launch_attn_tc(const Planes& qkv, float* ao, Planes* pl, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen) {
+  const int dk = Hc / L.heads;
+  AttnTcParams ap;
+  memset(&ap, 0, sizeof(ap));
+  REQUIRE(qkv.C == 3 * Hc, VTTS_ERR_INVALID, "qkv planes must hold 3*H channels");
+  ap.q_hi = make_map(qkv.hi, qkv.C, qkv.rows, ATC_BM);
+  ap.q_lo = make_map(qkv.lo, qkv.C, qkv.rows, ATC_BM);
+  ap.kv_hi = make_map(qkv.hi, qkv.C, qkv.rows, ATC_KT);
+  ap.kv_lo = make_map(qkv.lo, qkv.C, qkv.rows, ATC_KT);
+  ap.rk_hi = make_map(L.rk_hi, 128, ATC_RELP, ATC_RELP);
+  ap.rk_lo = make_map(L.rk_lo, 128, ATC_RELP, ATC_RELP);
+  ap.rv_hi = make_map(L.rv_hi, 128, ATC_RELP, ATC_RELP);
+  ap.rv_lo = make_map(L.rv_lo, 128, ATC_RELP, ATC_RELP);
+  ap.out = ao; ap.ldo = Hc;
+  ap.p_hi = pl ? pl->hi : nullptr; ap.p_lo = pl ? pl->lo : nullptr; ap.ldp = pl ? pl->C : 0;
+  ap.n_heads = L.heads; ap.window = cfg.window_size;
+  ap.koff = Hc; ap.voff = 2 * Hc;
+  dim3 grid((maxLen + ATC_BM - 1) / ATC_BM, L.heads, B);
+  if (grid.x == 0) return;
+  switch (dk / 32) {
+    case 1: klaunch(attn_tc_kernel<32>, grid, dim3(ATC_THREADS), (size_t)atc_smem_bytes(32), ap, lens, offs); break;
+    case 2: klaunch(attn_tc_kernel<64>, grid, dim3(ATC_THREADS), (size_t)atc_smem_bytes(64), ap, lens, offs); break;
+    case 3: klaunch(attn_tc_kernel<96>, grid, dim3(ATC_THREADS), (size_t)atc_smem_bytes(96), ap, lens, offs); break;
+    default: klaunch(attn_tc_kernel<128>, grid, dim3(ATC_THREADS), (size_t)atc_smem_bytes(128), ap, lens, offs); break;
+  }
+  CK(cudaGetLastError());
+  ++launches;
+}
+
 void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl) {
-  const int dk = Hc / cfg.n_heads, nrel = 2 * cfg.window_size + 1;
+  const int n_heads = L.heads;
+  const int dk = Hc / n_heads, nrel = 2 * cfg.window_size + 1;
   __nv_bfloat16* ph = pl ? pl->hi : nullptr;
   __nv_bfloat16* plo = pl ? pl->lo : nullptr;
   // register-blocked variant (4 query rows per warp) once the launch is throughput bound
   const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
   long rows = 0;
   for (int b = 0; b < B; ++b) rows += hl[b];
-  const int R = (attn_rows == 1 || attn_rows == 4) ? attn_rows : (rows * cfg.n_heads >= 8L * 2 * 148 * 4 ? 4 : 1);
+  const int R = (attn_rows == 1 || attn_rows == 4) ? attn_rows : (rows * n_heads >= 8L * 2 * 148 * 4 ? 4 : 1);
   // single short utterances: split-KV variant (all K/V tiles resident, 4 warps per query row) when it fits one wave
   {
     long ctas = 0;
-    for (int b = 0; b < B; ++b) ctas += (long)((hl[b] + ATS_ROWS - 1) / ATS_ROWS) * cfg.n_heads;
+    for (int b = 0; b < B; ++b) ctas += (long)((hl[b] + ATS_ROWS - 1) / ATS_ROWS) * n_heads;
     const int mt = (maxLen + AT_KT - 1) / AT_KT;
     if (attn_split && R == 1 && mt <= ATS_MAXT && ctas <= 148 && dk % 32 == 0 && dk <= 128) {
-      dim3 grid((maxLen + ATS_ROWS - 1) / ATS_ROWS, cfg.n_heads, B);
+      dim3 grid((maxLen + ATS_ROWS - 1) / ATS_ROWS, n_heads, B);
       const size_t smem = (size_t)attn_split_smem_floats(dk, nrel, mt) * sizeof(float);
-#define ATTN_SPLIT(D) klaunch(attn_split_kernel<D>, grid, dim3(ATS_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, mt, lens, offs, ph, plo)
+#define ATTN_SPLIT(D) klaunch(attn_split_kernel<D>, grid, dim3(ATS_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, mt, lens, offs, ph, plo)
       switch (dk / 32) { case 1: ATTN_SPLIT(1); break; case 2: ATTN_SPLIT(2); break; case 3: ATTN_SPLIT(3); break; default: ATTN_SPLIT(4); break; }
 #undef ATTN_SPLIT
       CK(cudaGetLastError());
@@ -768,9 +828,9 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
     }
   }
   const int QT = 8 * R;
-  dim3 grid((maxLen + QT - 1) / QT, cfg.n_heads, B);
+  dim3 grid((maxLen + QT - 1) / QT, n_heads, B);
   const size_t smem = (size_t)attn_smem_floats(dk, nrel, R) * sizeof(float);
-#define ATTN_CASE(D, RR) klaunch(attn_kernel<D, RR>, grid, dim3(AT_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, cfg.n_heads, cfg.window_size, lens, offs, ph, plo)
+#define ATTN_CASE(D, RR) klaunch(attn_kernel<D, RR>, grid, dim3(AT_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, lens, offs, ph, plo)
   if (R == 4) {
     switch (dk / 32) { case 1: ATTN_CASE(1, 4); break; case 2: ATTN_CASE(2, 4); break; case 3: ATTN_CASE(3, 4); break; default: ATTN_CASE(4, 4); break; }
   } else {
@@ -801,6 +861,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
   Planes ph = planes(slot++, F, H, zero), pao = planes(slot++, F, H, zero), ph1 = planes(slot++, F, H, zero);
   Planes pff = planes(slot++, F, H, zero), pwx = planes(slot++, F, H, zero), pacts = planes(slot++, F, H, zero);
   Planes pskip = planes(slot++, F, H, zero);
+  Planes pqkv = planes(slot++, F, 3 * H, zero);
   dim3 lg((maxFrm + 3) / 4, B);
   for (int f = nf - 1; f >= 0; --f) {
     const FlowW& W = flow[f];
@@ -814,9 +875,16 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
     }
     float* wn_x = h;
     if (c.use_transformer_flows) {
-      { TcSpec q; q.in = ph; q.w = W.t_qkv; q.bias = W.tr.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = fqkv; q.ldy = 3 * H;
-        launch_tc({q}, 1, fl, fo, maxFrm, B); }
-      launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, &pao);
+      if (attn_tc_ok(W.tr, H)) {
+        // q, k, v leave the qkv conv as split-bf16 planes only; attention runs on tcgen05 (attn_tc.cuh)
+        { TcSpec q; q.in = ph; q.w = W.t_qkv; q.bias = W.tr.qkv.b; q.Cin = H; q.Cout = 3 * H; q.out = pqkv; q.pl_slope = 1.f;
+          launch_tc({q}, 1, fl, fo, maxFrm, B); }
+        launch_attn_tc(pqkv, nullptr, &pao, W.tr, H, fl, fo, maxFrm);
+      } else {
+        { TcSpec q; q.in = ph; q.w = W.t_qkv; q.bias = W.tr.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = fqkv; q.ldy = 3 * H;
+          launch_tc({q}, 1, fl, fo, maxFrm, B); }
+        launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, &pao);
+      }
       { TcSpec q; q.in = pao; q.w = W.t_o; q.bias = W.tr.o.b; q.Cin = H; q.Cout = H; q.y = fy; q.ldy = H;
         launch_tc({q}, 1, fl, fo, maxFrm, B); }
       klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo);
@@ -1198,11 +1266,12 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   float* y = ensure(d_y, T * H);
   float* ffh = ensure(d_ffh, T * Fc);
   float* stats = ensure(d_stats, T * 2 * I);
-  Planes px, px1, pao, pff;
+  Planes px, px1, pao, pff, pqkv;
   if (enc_on_tc) {
     const bool zero = B > 1;
     px = planes(60, (long)T, H, zero); px1 = planes(61, (long)T, H, zero);
     pao = planes(62, (long)T, H, zero); pff = planes(63, (long)T, Fc, zero);
+    pqkv = planes(59, (long)T, 3 * H, zero);
   }
   {
     dim3 g(maxTok, B);
@@ -1221,9 +1290,15 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     const EncLayerW& L = enc[i];
     const int ks = c.kernel_size;
     dim3 lg((maxTok + 3) / 4, B);
-    { TcSpec q; q.in = px; q.w = L.t_qkv; q.bias = L.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = qkv; q.ldy = 3 * H;
-      launch_tc({q}, 1, tl, to, maxTok, B); }
-    launch_attn(qkv, ao, L, H, tl, to, maxTok, &pao);
+    if (attn_tc_ok(L, H)) {
+      { TcSpec q; q.in = px; q.w = L.t_qkv; q.bias = L.qkv.b; q.Cin = H; q.Cout = 3 * H; q.out = pqkv; q.pl_slope = 1.f;
+        launch_tc({q}, 1, tl, to, maxTok, B); }
+      launch_attn_tc(pqkv, nullptr, &pao, L, H, tl, to, maxTok);
+    } else {
+      { TcSpec q; q.in = px; q.w = L.t_qkv; q.bias = L.qkv.b; q.Cin = H; q.Cout = 3 * H; q.y = qkv; q.ldy = 3 * H;
+        launch_tc({q}, 1, tl, to, maxTok, B); }
+      launch_attn(qkv, ao, L, H, tl, to, maxTok, &pao);
+    }
     { TcSpec q; q.in = pao; q.w = L.t_o; q.bias = L.o.b; q.Cin = H; q.Cout = H; q.y = y; q.ldy = H;
       launch_tc({q}, 1, tl, to, maxTok, B); }
     klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, x, y, L.ln1.g, L.ln1.b, (const float*)nullptr, (const float*)nullptr, 0, xb, tl, to, H, px1.hi, px1.lo);
@@ -1845,6 +1920,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
+    if (const char* e = getenv("VTTS_ATTN_TC")) h->attn_tc = atoi(e) != 0;
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
@@ -1852,6 +1928,10 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->bind_weights();
     h->build_prefetch_list();
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(32)));
+    CK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(64)));
+    CK(cudaFuncSetAttribute(attn_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(96)));
+    CK(cudaFuncSetAttribute(attn_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(128)));
     CK(cudaFuncSetAttribute(attn_split_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(attn_split_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CK(cudaFuncSetAttribute(attn_split_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -2106,6 +2186,65 @@ int vtts_debug_read(vtts_handle h, const char* name, float* out, size_t max_floa
     CK(cudaMemcpyAsync(out, src, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     *n_out = n;
+  });
+}
+
+// Unit-test hook: runs ONE attention launch of the named encoder layer ("enc.<i>" or "flow.<f>.tr") on a caller-supplied
+// fp32 qkv tensor [T][3H] of a single utterance and returns the fp32 output [T][H].  use_tc = 1: attn_tc_kernel on the
+// split-bf16 planes of the input (needs a precision >= 1 engine); 0: the fp32 FFMA kernels.  iters > 0 also times the launch.
+int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host, int T, int use_tc, float* out_host, int iters,
+                         float* ms_out) {
+  if (!layer || !qkv_host || !out_host || T < 1) return VTTS_ERR_INVALID;
+  return guarded(h, [&] {
+    const std::string nm(layer);
+    const EncLayerW* L = nullptr;
+    if (nm.rfind("enc.", 0) == 0) {
+      const int i = atoi(nm.c_str() + 4);
+      REQUIRE(i >= 0 && i < (int)h->enc.size(), VTTS_ERR_INVALID, "no such encoder layer");
+      L = &h->enc[i];
+    } else if (nm.rfind("flow.", 0) == 0) {
+      const int f = atoi(nm.c_str() + 5);
+      REQUIRE(f >= 0 && f < (int)h->flow.size() && h->cfg.use_transformer_flows, VTTS_ERR_INVALID, "no such flow layer");
+      L = &h->flow[f].tr;
+    }
+    REQUIRE(L != nullptr, VTTS_ERR_INVALID, "layer must be enc.<i> or flow.<f>.tr");
+    const int H = h->cfg.hidden_channels;
+    REQUIRE(!use_tc || h->attn_tc_ok(*L, H), VTTS_ERR_INVALID, "tensor-core attention is not available for this layer / precision mode");
+    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len; const int mf0 = h->maxFrm;
+    h->B = 1; h->h_frm_len.assign(1, T); h->h_tok_len.assign(1, T); h->maxFrm = T;
+    int* dl = nullptr; float *dq = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&dl, 16));
+    const int hl[3] = {T, 0, T};
+    CK(cudaMemcpy(dl, hl, 12, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dq, (size_t)T * 3 * H * 4)); CK(cudaMalloc(&dout, (size_t)T * H * 4));
+    CK(cudaMemcpy(dq, qkv_host, (size_t)T * 3 * H * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dout, 0, (size_t)T * H * 4));
+    Planes pq;
+    if (use_tc) {
+      pq = h->planes(58, T, 3 * H, false);
+      h->klaunch(split_planes_kernel, dim3(T, 1), dim3(64), (size_t)0, (const float*)dq, 3 * H, pq.hi, pq.lo, 3 * H, 3 * H, 1.f, 0, 1, (const int*)dl, (const int*)(dl + 1));
+    }
+    auto once = [&] {
+      if (use_tc) h->launch_attn_tc(pq, dout, nullptr, *L, H, dl, dl + 1, T);
+      else h->launch_attn(dq, dout, *L, H, dl, dl + 1, T, nullptr);
+    };
+    once();
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(out_host, dout, (size_t)T * H * 4, cudaMemcpyDeviceToHost));
+    if (iters > 0 && ms_out) {
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      CK(cudaEventRecord(e0, h->stream));
+      for (int i = 0; i < iters; ++i) once();
+      CK(cudaEventRecord(e1, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      float ms = 0.f;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      *ms_out = ms / iters;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    cudaFree(dl); cudaFree(dq); cudaFree(dout);
+    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0; h->maxFrm = mf0;
   });
 }
 

@@ -261,6 +261,9 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   Lphys = lens[b] * cb.rmul;
   L = Lphys + P.in_extra;
   if (t0 >= L) return;                  // uniform over the cluster (pending cp.async into our own smem is harmless)
+  // Distributed shared memory may only be touched once the owning CTA is known to be running: every CTA announces itself
+  // here (non-blocking) and the matching wait sits right before the first remote store of the split-K reduction
+  if (S > 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n" ::: "memory");
   in_base = (long)offs[b] * cb.rmul;
   out_base = in_base * P.out_mul + (long)b * P.out_seq_extra;
   int xbuf = 0;        // Xs buffer holding the chunk of the current step
@@ -331,6 +334,7 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
   if (S > 1) {
     const int ne4 = 8 / S;                                 // units per owner
     float4* stage = reinterpret_cast<float4*>(smem + cb.stage_off);
+    asm volatile("barrier.cluster.wait.aligned;\n" ::: "memory");   // all peers have started (announced at kernel entry)
     if (grp == 0) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {

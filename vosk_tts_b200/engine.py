@@ -34,7 +34,7 @@ class VttsConfig(C.Structure):
         ("n_upsamples", C.c_int32), ("upsample_rates", C.c_int32 * 8), ("upsample_kernel_sizes", C.c_int32 * 8),
         ("upsample_initial_channel", C.c_int32),
         ("subbands", C.c_int32), ("istft_n_fft", C.c_int32), ("istft_hop", C.c_int32),
-        ("precision", C.c_int32),
+        ("precision", C.c_int32), ("flow_n_heads", C.c_int32),
     ]
 
 
@@ -43,7 +43,7 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
            "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev",
-           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk"]
+           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention"]
 
 
 def lib_path():
@@ -112,6 +112,8 @@ def load_library(build_if_missing=True):
     lib.vtts_profile_read.restype = i32
     lib.vtts_profile_read_tc.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
     lib.vtts_profile_read_tc.restype = i32
+    lib.vtts_debug_attention.argtypes = [vp, C.c_char_p, vp, i32, i32, vp, i32, fp]
+    lib.vtts_debug_attention.restype = i32
     _LIB = lib
     return lib
 
@@ -147,6 +149,7 @@ def make_c_config(cfg, precision=0):
     c.istft_n_fft = int(cfg["gen_istft_n_fft"])
     c.istft_hop = int(cfg["gen_istft_hop_size"])
     c.precision = int(precision)
+    c.flow_n_heads = int(cfg.get("flow_n_heads", 2))
     return c
 
 
@@ -345,6 +348,15 @@ class Engine:
         self._check(self.lib.vtts_profile_read_tc(self.h, C.byref(ms), C.byref(n), C.byref(fl)))
         out.update(tc_ms=ms.value, tc_launches=int(n.value), tc_flops=fl.value)
         return out
+
+    def debug_attention(self, layer, qkv, use_tc, iters=0):
+        """One attention launch of `layer` ("enc.<i>" / "flow.<f>.tr") on qkv float32 [T, 3H]; returns (out [T, H], ms or None)."""
+        qkv = np.ascontiguousarray(qkv, dtype=np.float32)
+        T, H = qkv.shape[0], qkv.shape[1] // 3
+        out = np.zeros((T, H), np.float32)
+        ms = C.c_float(0.0)
+        self._check(self.lib.vtts_debug_attention(self.h, layer.encode(), _ptr(qkv), T, int(use_tc), _ptr(out), int(iters), C.byref(ms)))
+        return out, (float(ms.value) if iters > 0 else None)
 
     def debug_flags(self, flags):
         self._check(self.lib.vtts_debug_flags(self.h, int(flags)))

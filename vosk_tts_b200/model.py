@@ -62,8 +62,9 @@ class Model:
         cks = sorted(glob.glob(str(model_path / "G_*.pth")), key=lambda p: int(re.sub(r"\D", "", os.path.basename(p)) or 0))
         if (model_path / "model.pth").exists():
             cks.append(str(model_path / "model.pth"))
-        if not cks and (model_path / "model.onnx").exists():
-            # the deployed layout (vosk_tts/model.py:46): everything comes out of the graph
+        if (model_path / "model.onnx").exists():
+            # the deployed layout (vosk_tts/model.py:46): everything comes out of the graph.  Preferred over a checkpoint
+            # lying next to it: model.onnx is what the reference itself would load, and it is not a pickle
             from . import onnx_weights as _onnx
             sr = int(self.config.get("audio", {}).get("sample_rate", 22050))
             cfg = _onnx.config_from_onnx(str(model_path / "model.onnx"), sampling_rate=sr)

@@ -29,9 +29,14 @@ def fold_weight_norm(sd):
     return out
 
 
-def load_checkpoint(path):
-    """Reads a reference ``G_*.pth`` (utils.py:18-21) and returns the folded state dict."""
-    ck = torch.load(path, map_location="cpu", weights_only=False)
+def load_checkpoint(path, allow_pickle=False):
+    """Reads a reference ``G_*.pth`` (utils.py:18-21) and returns the folded state dict.
+
+    The ``{'model': state_dict, 'iteration': int, 'optimizer': ..., 'learning_rate': float}`` layout is plain tensors
+    and numbers, so the file is read with ``weights_only=True``: a crafted checkpoint in a model directory cannot run
+    code at load time (the reference's inference package only ever opens ``model.onnx``).  ``allow_pickle=True`` is an
+    explicit opt-in for legacy files that need full unpickling."""
+    ck = torch.load(path, map_location="cpu", weights_only=not allow_pickle)
     sd = ck["model"] if isinstance(ck, dict) and "model" in ck else ck
     sd = {k[len("module."):] if k.startswith("module.") else k: v for k, v in sd.items()}
     return fold_weight_norm(sd)
@@ -193,6 +198,18 @@ def pack(w, cfg, tc=True):
             P.conv_tc(dst + ".ffn2", g(f_ + ".conv_2.weight"))
         P.add(dst + ".relk", g(a + ".emb_rel_k")[0])
         P.add(dst + ".relv", g(a + ".emb_rel_v")[0])
+        if with_tc:
+            # the same tables as split-bf16 [16 offsets][128 channels] tiles (zero padded) for the tcgen05 attention:
+            # Ek is a K-major B operand of Q Ek^T, Ev an MN-major B operand of P_band Ev (csrc/attn_tc.cuh)
+            for nm, src_t in ((".rk", g(a + ".emb_rel_k")[0]), (".rv", g(a + ".emb_rel_v")[0])):
+                nrel, dk = src_t.shape
+                if nrel <= 16 and dk <= 128:
+                    t = np.zeros((16, 128), np.float32)
+                    t[:nrel, :dk] = src_t
+                    hi = to_bf16_bits(t)
+                    lo = to_bf16_bits(t - from_bf16_bits(hi))
+                    P.add(dst + nm + "h", hi.reshape(-1).view(np.float32))
+                    P.add(dst + nm + "l", lo.reshape(-1).view(np.float32))
         ln(dst + ".ln1", "%s.norm_layers_1.%d" % (src, i))
         f = "%s.ffn_layers.%d" % (src, i)
         P.conv(dst + ".ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"))
