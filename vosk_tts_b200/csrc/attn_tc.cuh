@@ -349,8 +349,13 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
         m_run = mx;
         need = true;
       }
+      // pv_done completes one phase per key tile and a parity wait can only tell the current phase from the one before it:
+      // every thread therefore observes EVERY phase, in order -- here when O has to be rescaled, otherwise just before this
+      // tile's P is handed over (by then the P V MMAs of tile t-1 have normally retired, so the wait costs nothing)
+      bool pv_seen = (t == 0);
       if (__any_sync(0xffffffffu, need)) {           // warp-uniform: tcgen05.ld/st are warp collectives
         mbar_wait(pv_done, (t - 1) & 1);             // the P V MMAs of tile t-1 have retired: O is quiescent
+        pv_seen = true;
         tc_fence_after();
         l_run *= alpha;
 #pragma unroll
@@ -414,6 +419,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
         tmem_st_x8(pb, bh);
         tmem_st_x8(pb + 8, bl);
       }
+      if (!pv_seen) mbar_wait(pv_done, (t - 1) & 1);
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[bsel]);

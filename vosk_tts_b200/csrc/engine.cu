@@ -10,6 +10,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <initializer_list>
+#include <map>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -169,7 +171,54 @@ struct vtts_engine {
   size_t tc_prof_used = 0;
 
   // ---- per-call state
+  // Ttok / maxTok / Tfrm / maxFrm are the BUCKETED row counts that size buffers, grids, tensor maps and captured graphs
+  // (== the real ones with VTTS_BUCKETS=0); the kernels themselves read the true lengths / offsets from device memory.
+  // real_* hold the true values for host-side copies; v_*_len are virtual per-utterance lengths (functions of the buckets
+  // only) for the launch heuristics, so that a graph captured for a bucket is valid for every call that maps to it.
   int B = 0, Ttok = 0, maxTok = 0, Tfrm = 0, maxFrm = 0;
+  int real_Ttok = 0, real_maxTok = 0, real_Tfrm = 0, real_maxFrm = 0;
+  std::vector<int> v_tok_len, v_frm_len;
+  bool use_buckets = true;
+  int eps_dp_ld = 0;                 // row pitch of the duration-predictor noise the phase-1 kernels read
+  static int bucket_tok(int n) { return n <= 256 ? (n + 15) / 16 * 16 : (n + 63) / 64 * 64; }
+  static int bucket_frm(int n) { return n <= 512 ? (n + 31) / 32 * 32 : (n <= 4096 ? (n + 127) / 128 * 128 : (n + 511) / 512 * 512); }
+  static void virtual_lens(std::vector<int>& v, int nB, int total_cap, int max_cap) {
+    const int per = std::max(1, std::min(max_cap, (total_cap - (nB - 1) * SEQ_GAP + nB - 1) / nB));
+    v.assign(nB, per);
+  }
+  void set_token_shape() {      // from h_tok_len / h_tok_off (real)
+    real_Ttok = h_tok_off[B];
+    real_maxTok = 0;
+    for (int b = 0; b < B; ++b) real_maxTok = std::max(real_maxTok, h_tok_len[b]);
+    if (use_buckets) {
+      maxTok = bucket_tok(real_maxTok);
+      Ttok = B == 1 ? maxTok : (real_Ttok + 63) / 64 * 64;
+    } else { maxTok = real_maxTok; Ttok = real_Ttok; }
+    virtual_lens(v_tok_len, B, Ttok, maxTok);
+    if (!use_buckets) v_tok_len = h_tok_len;
+  }
+  void set_frame_shape() {      // from h_frm_len / h_frm_off (real)
+    real_Tfrm = h_frm_off[B];
+    real_maxFrm = 0;
+    for (int b = 0; b < B; ++b) real_maxFrm = std::max(real_maxFrm, h_frm_len[b]);
+    if (use_buckets) {
+      maxFrm = bucket_frm(real_maxFrm);
+      Tfrm = B == 1 ? std::max(maxFrm, real_Tfrm) : (real_Tfrm <= 8192 ? (real_Tfrm + 255) / 256 * 256 : (real_Tfrm + 1023) / 1024 * 1024);
+    } else { maxFrm = real_maxFrm; Tfrm = real_Tfrm; }
+    virtual_lens(v_frm_len, B, Tfrm, maxFrm);
+    if (!use_buckets) v_frm_len = h_frm_len;
+  }
+  // plane buffers whose rows behind each utterance must be zeroed for this phase (see zero_tails_kernel)
+  TailList tail;
+  bool collecting = false;
+  void begin_planes() { tail.n = 0; collecting = true; }
+  void flush_tails(const int* lens, const int* offs) {
+    collecting = false;
+    if (tail.n == 0) return;
+    klaunch(zero_tails_kernel, dim3(tail.n, B), dim3(128), (size_t)0, tail, lens, offs, B);
+    CK(cudaGetLastError());
+    ++launches;
+  }
   bool have_durations = false;
   float scales[3] = {0.f, 1.f, 0.f};
   uint64_t seed = 0;
@@ -198,7 +247,7 @@ struct vtts_engine {
   bool use_poll = true;
   // CUDA graphs: a call shape seen before is captured once and replayed (launch-bound at batch 1)
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
-  std::unordered_map<uint64_t, GraphEntry> graphs;
+  std::map<std::vector<long long>, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
   int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1;
@@ -242,12 +291,27 @@ struct vtts_engine {
   char* ensure_pinned(size_t n) { return ensure_pinned(h_pin, n); }
 
   // Runs `enqueue` (which only enqueues work on `stream`) eagerly the first time a shape key is seen, captures it
-  // into a CUDA graph the second time, and replays the graph afterwards.
+  // into a CUDA graph the second time, and replays the graph afterwards.  The key is the full tuple of everything the
+  // enqueued work depends on besides device-resident data (phase tag, batch, length buckets, noise mode, raw pointers of
+  // the *_dev entry points): entries are compared on the tuple itself, so there is no hash collision to replay a wrong
+  // graph on.  The cache is bounded (LRU, checked on every insertion).
+  static constexpr size_t GRAPH_CACHE_MAX = 48;
   template <typename Fn>
-  void run_graphed(uint64_t key, Fn&& enqueue) {
+  void run_graphed(std::initializer_list<long long> key_il, Fn&& enqueue) {
     last_graphed = false;
     if (!use_graphs || profiling || debug_flags) { enqueue(); return; }
-    GraphEntry& g = graphs[key];
+    const std::vector<long long> key(key_il);
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      if (graphs.size() >= GRAPH_CACHE_MAX) {       // evict the least recently used entry before inserting
+        auto old = graphs.begin();
+        for (auto k = graphs.begin(); k != graphs.end(); ++k) if (k->second.used < old->second.used) old = k;
+        if (old->second.exec) cudaGraphExecDestroy(old->second.exec);
+        graphs.erase(old);
+      }
+      it = graphs.emplace(key, GraphEntry{}).first;
+    }
+    GraphEntry& g = it->second;
     if (g.exec && g.gen != ws_gen) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; g.seen = 0; }
     g.used = ++graph_clock;
     if (g.exec) {
@@ -282,11 +346,6 @@ struct vtts_engine {
     CK(cudaGraphLaunch(g.exec, stream));
     ++graph_replays;
     last_graphed = true;
-    if (graphs.size() > 64) {                  // bounded cache: drop the least recently used entry
-      uint64_t oldest = ~0ull, okey = 0;
-      for (auto& kv : graphs) if (kv.second.used < oldest) { oldest = kv.second.used; okey = kv.first; }
-      if (okey != key) { if (graphs[okey].exec) cudaGraphExecDestroy(graphs[okey].exec); graphs.erase(okey); }
-    }
   }
   // Every kernel goes through here: programmatic dependent launch lets the next kernel's prologue overlap this one's tail.
   template <typename... KArgs, typename... Args>
@@ -371,8 +430,9 @@ struct vtts_engine {
     REQUIRE(Cin % TC_BK == 0, VTTS_ERR_INVALID, "tensor-core conv needs input channels in multiples of 64");
     return t;
   }
-  Planes planes(int slot, long rows, int C, bool zero) {
+  Planes planes(int slot, long units, int rm, int C, int extra = 0) {
     Planes p;
+    const long rows = units * rm + (extra ? (long)B * extra : 0);
     p.C = C; p.rows = rows;
     const size_t n = (size_t)rows * C + 64;
     REQUIRE(slot >= 0 && 2 * slot + 1 < 128, VTTS_ERR_INVALID, "plane slot out of range");
@@ -383,9 +443,10 @@ struct vtts_engine {
     // tile) are multiplied by exact zeros in the attention's P V product, so they must at least be finite
     if (pl_pool[2 * slot].cap != cap_hi) CK(cudaMemsetAsync(p.hi, 0, pl_pool[2 * slot].cap * sizeof(__nv_bfloat16), stream));
     if (pl_pool[2 * slot + 1].cap != cap_lo) CK(cudaMemsetAsync(p.lo, 0, pl_pool[2 * slot + 1].cap * sizeof(__nv_bfloat16), stream));
-    if (zero) {     // gap rows between packed utterances must read as zero through TMA
-      CK(cudaMemsetAsync(p.hi, 0, n * sizeof(__nv_bfloat16), stream));
-      CK(cudaMemsetAsync(p.lo, 0, n * sizeof(__nv_bfloat16), stream));
+    if (collecting) {   // rows behind each utterance must read as zero through TMA: zeroed by one zero_tails launch per phase
+      REQUIRE(tail.n < ZT_MAXP && C % 8 == 0, VTTS_ERR_INVALID, "too many plane buffers in one phase");
+      TailList::E& e = tail.e[tail.n++];
+      e.hi = p.hi; e.lo = p.lo; e.C = C; e.rm = rm; e.extra = extra; e.rows_cap = (int)rows;
     }
     return p;
   }
@@ -409,6 +470,12 @@ struct vtts_engine {
   void phase1(const int* ids_packed_host, const int64_t* d_ids64, int t_max, const int64_t* d_sid64, const int* sid_host,
               const float* noise_dp, bool noise_on_device);
   void phase2(const float* noise_z, int z_ld, bool noise_on_device, bool run_decoder = true);
+  void stage_noise_z(const float* noise_z, int z_ld) {       // caller memory (maybe pageable) -> pinned [B][I][maxFrm]
+    const int I = cfg.inter_channels;
+    float* pin = reinterpret_cast<float*>(ensure_pinned(h_pin_z, (size_t)B * I * maxFrm * sizeof(float)));
+    const size_t ncopy = (size_t)std::min(z_ld, maxFrm);
+    for (long r = 0; r < (long)B * I; ++r) memcpy(pin + r * maxFrm, noise_z + r * (long)z_ld, ncopy * sizeof(float));
+  }
   void decode(float* z, const int* fl, const int* fo);
   bool have_latent = false;
   Buf<int> d_chunk;                              // [len, off, off_end] of the chunk being decoded
@@ -621,7 +688,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   // count: used once the launch still fills the machine (batched calls), or when forced (VTTS_TC_BN).
   int BN = 64;
   {
-    const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+    const std::vector<int>& hl = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
     long ctas128 = 0;
     bool wide = true;
     for (const TcSpec& q : ps) {
@@ -662,7 +729,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   // wider split than 64-wide ones (same k-steps per CTA-step, half the CTAs per tile row).
   int split = 1;
   if (!tall && tc_split != 1) {
-    const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+    const std::vector<int>& hl = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
     long active[2] = {0, 0};
     int minsteps = 1 << 30;
     bool wide = true;
@@ -727,7 +794,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     }
     for (const TcSpec& q : ps)
       for (int b = 0; b < nB; ++b)
-        tc_prof_flops += 2.0 * ((double)((lens == d_tok_len.p) ? h_tok_len[b] : h_frm_len[b]) * rmul + q.in_extra) * q.Cout * q.Cin * q.k;
+        tc_prof_flops += 2.0 * ((double)((lens == d_tok_len.p) ? h_tok_len[b] : h_frm_len[b]) * rmul + q.in_extra) * q.Cout * q.Cin * q.k;   // (true lengths)
     ++tc_prof_launches;
     CK(cudaEventRecord(tc_prof_ev[tc_prof_used], stream));
   }
@@ -807,7 +874,7 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
   __nv_bfloat16* ph = pl ? pl->hi : nullptr;
   __nv_bfloat16* plo = pl ? pl->lo : nullptr;
   // register-blocked variant (4 query rows per warp) once the launch is throughput bound
-  const std::vector<int>& hl = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+  const std::vector<int>& hl = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
   long rows = 0;
   for (int b = 0; b < B; ++b) rows += hl[b];
   const int R = (attn_rows == 1 || attn_rows == 4) ? attn_rows : (rows * n_heads >= 8L * 2 * 148 * 4 ? 4 : 1);
@@ -848,7 +915,6 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
   const vtts_config& c = cfg;
   const int H = c.hidden_channels, I = c.inter_channels, half = I / 2;
   const long F = Tfrm;
-  const bool zero = B > 1;
   const int nf = c.flow_n_flows, nl = c.flow_wn_layers, fk = c.flow_kernel_size;
   float* h = ensure(d_h, (size_t)F * H);
   float* h1 = ensure(d_h1, (size_t)F * H);
@@ -858,10 +924,12 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
   float* fqkv = ensure(d_fqkv, (size_t)F * 3 * H);
   float* fao = ensure(d_fao, (size_t)F * H);
   int slot = 40;    // plane slots 40.. are the flow's (the decoder uses 0..)
-  Planes ph = planes(slot++, F, H, zero), pao = planes(slot++, F, H, zero), ph1 = planes(slot++, F, H, zero);
-  Planes pff = planes(slot++, F, H, zero), pwx = planes(slot++, F, H, zero), pacts = planes(slot++, F, H, zero);
-  Planes pskip = planes(slot++, F, H, zero);
-  Planes pqkv = planes(slot++, F, 3 * H, zero);
+  begin_planes();
+  Planes ph = planes(slot++, F, 1, H), pao = planes(slot++, F, 1, H), ph1 = planes(slot++, F, 1, H);
+  Planes pff = planes(slot++, F, 1, H), pwx = planes(slot++, F, 1, H), pacts = planes(slot++, F, 1, H);
+  Planes pskip = planes(slot++, F, 1, H);
+  Planes pqkv = planes(slot++, F, 1, 3 * H);
+  flush_tails(fl, fo);
   dim3 lg((maxFrm + 3) / 4, B);
   for (int f = nf - 1; f >= 0; --f) {
     const FlowW& W = flow[f];
@@ -931,10 +999,26 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
   const vtts_config& c = cfg;
   const int I = c.inter_channels;
   const long F = Tfrm;
-  const bool zero = B > 1;
   const int nk = c.n_resblock_kernels, nd = c.n_resblock_dilations;
   int slot = 0;
-  Planes pz = planes(slot++, F, I, zero);
+  // every plane buffer of the decoder, allocated (and its tails zeroed) before the first launch
+  begin_planes();
+  Planes pz = planes(slot++, F, 1, I);
+  Planes cur = planes(slot++, F, 1, c.upsample_initial_channel);
+  std::vector<Planes> st_px(c.n_upsamples), st_nxt(c.n_upsamples);
+  std::vector<std::vector<Planes>> st_pj(c.n_upsamples), st_pt(c.n_upsamples);
+  {
+    int rmp = 1, chp = c.upsample_initial_channel;
+    for (int i = 0; i < c.n_upsamples; ++i) {
+      rmp *= c.upsample_rates[i];
+      chp /= 2;
+      st_px[i] = planes(slot++, F, rmp, chp);
+      st_pj[i].resize(nk); st_pt[i].resize(nk);
+      for (int j = 0; j < nk; ++j) { st_pj[i][j] = planes(slot++, F, rmp, chp); st_pt[i][j] = planes(slot++, F, rmp, chp); }
+      st_nxt[i] = planes(slot++, F, rmp, chp, (i + 1 == c.n_upsamples) ? 1 : 0);
+    }
+  }
+  flush_tails(fl, fo);
   {
     dim3 g(maxFrm, B);
     klaunch(split_planes_kernel, dim3(g), dim3(64), (size_t)(0), z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
@@ -942,7 +1026,6 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
     ++launches;
   }
   int ch = c.upsample_initial_channel;
-  Planes cur = planes(slot++, F, ch, zero);
   {
     TcSpec q;
     q.in = pz; q.w = tc_pre; q.bias = dec_pre.b; q.Cin = I; q.Cout = ch; q.k = 7; q.dil = 1; q.pad = 3;
@@ -962,7 +1045,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
     const int u = c.upsample_rates[i], ch2 = ch / 2;
     const long rows = F * rm * u;
     float* X = ensure(d_stage[i], (size_t)rows * ch2);
-    Planes px = planes(slot++, rows, ch2, zero);
+    Planes px = st_px[i];
     for (int r0 = 0; r0 < u; r0 += TC_MAXP) {
       std::vector<TcSpec> ps;
       for (int r = r0; r < std::min(u, r0 + TC_MAXP); ++r) {
@@ -980,8 +1063,8 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
     std::vector<Planes> pj(nk), pt(nk);
     for (int j = 0; j < nk; ++j) {
       xj[j] = ensure(d_xj[i][j], (size_t)rows * ch);
-      pj[j] = planes(slot++, rows, ch, zero);
-      pt[j] = planes(slot++, rows, ch, zero);
+      pj[j] = st_pj[i][j];
+      pt[j] = st_pt[i][j];
     }
     auto rb_pair = [&](int j, int d, TcSpec& a, TcSpec& b2) {
       const RbW& R = rbs[i * nk + j];
@@ -998,7 +1081,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
     // the split-K width that suits its own k-loop -- correct, but the concurrent cluster launches of three streams
     // contend and the step gets slower (1.74 vs 1.62 ms).
     long group_tiles = 0;
-    for (int b = 0; b < B; ++b) group_tiles += (long)nk * ((h_frm_len[b] * rm + TC_BM - 1) / TC_BM) * ((ch + 63) / 64);
+    for (int b = 0; b < B; ++b) group_tiles += (long)nk * ((v_frm_len[b] * rm + TC_BM - 1) / TC_BM) * ((ch + 63) / 64);
     const bool branch = mrf_branch && !profiling && nk > 1 && nk - 1 <= 3 && group_tiles <= 148;
     if (branch) {
       struct Restore { cudaStream_t& s; cudaStream_t v; ~Restore() { s = v; } } restore{stream, stream};
@@ -1030,7 +1113,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
       }
     }
     const bool last = (i + 1 == c.n_upsamples);
-    Planes nxt = planes(slot++, rows + (last ? B : 0), ch, zero);
+    Planes nxt = st_nxt[i];
     {
       dim3 g(maxFrm * rm + (last ? 1 : 0), B);
       klaunch(mrf_mean_planes_kernel, dim3(g), dim3(32), (size_t)(0), xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
@@ -1075,7 +1158,8 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   }
   cb.n = (int)ps.size();
   cb.rmul = rmul;
-  const std::vector<int>& hl0 = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
+  const std::vector<int>& hl0 = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
+  const std::vector<int>& hl_true = (lens == d_tok_len.p) ? h_tok_len : h_frm_len;
   long base0 = 0;
   for (const ConvP& q : ps)
     for (int b = 0; b < nB; ++b) base0 += (long)((hl0[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
@@ -1107,7 +1191,7 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   const size_t stage_off = (std::max(pipe_floats, red_floats) + 3) / 4 * 4;
   cb.stage_off = (int)stage_off;
   const size_t smem = (stage_off + (S > 1 ? (size_t)32 * CV_THREADS : 0)) * sizeof(float);
-  const std::vector<int>& hl = hl0;
+  const std::vector<int>& hl = hl_true;      // (profiling FLOP count below)
   dim3 grid(((maxL + CV_TT - 1) / CV_TT) * S, (maxCout + CV_TC - 1) / CV_TC, nB * cb.n);
   if (grid.x == 0) return;
   if (profiling) {
@@ -1233,9 +1317,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
       CK(cudaGetLastError());
       launches += 2;
     }
-    if (noise_dp && !noise_on_device) {
-      float* de = ensure(d_eps_dp, (size_t)B * 2 * t_max);
-      CK(cudaMemcpyAsync(de, pp.eps, (size_t)B * 2 * t_max * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (noise_dp && !noise_on_device) {      // staged as [B][2][maxTok] (stage1)
+      float* de = ensure(d_eps_dp, (size_t)B * 2 * maxTok);
+      CK(cudaMemcpyAsync(de, pp.eps, (size_t)B * 2 * maxTok * sizeof(float), cudaMemcpyHostToDevice, stream));
       noise_dp = de;
     }
   }
@@ -1268,10 +1352,11 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   float* stats = ensure(d_stats, T * 2 * I);
   Planes px, px1, pao, pff, pqkv;
   if (enc_on_tc) {
-    const bool zero = B > 1;
-    px = planes(60, (long)T, H, zero); px1 = planes(61, (long)T, H, zero);
-    pao = planes(62, (long)T, H, zero); pff = planes(63, (long)T, Fc, zero);
-    pqkv = planes(59, (long)T, 3 * H, zero);
+    begin_planes();
+    px = planes(60, (long)T, 1, H); px1 = planes(61, (long)T, 1, H);
+    pao = planes(62, (long)T, 1, H); pff = planes(63, (long)T, 1, Fc);
+    pqkv = planes(59, (long)T, 1, 3 * H);
+    flush_tails(tl, to);
   }
   {
     dim3 g(maxTok, B);
@@ -1335,7 +1420,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   }
   {
     dim3 g((maxTok + 127) / 128, B);
-    klaunch(dp_noise_kernel, dim3(g), dim3(128), (size_t)(0), noise_dp, t_max, prm, za, zb, tl, to);
+    klaunch(dp_noise_kernel, dim3(g), dim3(128), (size_t)(0), noise_dp, eps_dp_ld, prm, za, zb, tl, to);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -1391,8 +1476,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
 // Host side of phase 1: stage the call's inputs in pinned memory (fixed layout, so a captured graph can re-read it).
 vtts_engine::P1Pin vtts_engine::p1_layout(int t_max, bool eps) {
   const size_t T = (size_t)Ttok;
+  (void)t_max;
   const size_t bytes = (size_t)(3 * B + 1) * sizeof(int) + T * sizeof(int) + 8 * sizeof(float) +
-                       (eps ? (size_t)B * 2 * t_max * sizeof(float) : 0) + 64;
+                       (eps ? (size_t)B * 2 * maxTok * sizeof(float) : 0) + 64;
   char* pin = ensure_pinned(h_pin_in, bytes);
   P1Pin pp;
   pp.len = reinterpret_cast<int*>(pin);
@@ -1409,7 +1495,7 @@ void vtts_engine::stage1(const int* ids_packed_host, const int* sid_host, int t_
   memcpy(pp.len, h_tok_len.data(), B * sizeof(int));
   memcpy(pp.off, h_tok_off.data(), (B + 1) * sizeof(int));
   if (ids_packed_host) {
-    memcpy(pp.ids, ids_packed_host, (size_t)Ttok * sizeof(int));
+    memcpy(pp.ids, ids_packed_host, (size_t)real_Ttok * sizeof(int));
     memcpy(pp.sid, sid_host, B * sizeof(int));
   }
   pp.prm[0] = scales[0]; pp.prm[1] = scales[1]; pp.prm[2] = scales[2]; pp.prm[3] = 0.f;
@@ -1433,7 +1519,11 @@ void vtts_engine::stage1(const int* ids_packed_host, const int* sid_host, int t_
     pp.prm[6] = 0.f;
   }
   pp.prm[7] = 0.f;
-  if (noise_dp_host) memcpy(pp.eps, noise_dp_host, (size_t)B * 2 * t_max * sizeof(float));
+  if (noise_dp_host) {        // [B][2][t_max] -> [B][2][maxTok]: the device layout depends on the length bucket only
+    for (int r = 0; r < 2 * B; ++r)
+      memcpy(pp.eps + (size_t)r * maxTok, noise_dp_host + (size_t)r * t_max, (size_t)std::min(t_max, maxTok) * sizeof(float));
+    eps_dp_ld = maxTok;
+  }
 }
 
 void vtts_engine::finish1() {
@@ -1451,9 +1541,7 @@ void vtts_engine::finish1() {
     }
     h_frm_len.assign(h_map + 1, h_map + 1 + B);
     h_frm_off.assign(h_map + 1 + B, h_map + 1 + 2 * B + 1);
-    Tfrm = h_frm_off[B];
-    maxFrm = 0;
-    for (int b = 0; b < B; ++b) maxFrm = std::max(maxFrm, h_frm_len[b]);
+    set_frame_shape();
     have_durations = true;
     return;
   }
@@ -1461,9 +1549,7 @@ void vtts_engine::finish1() {
   const int* p_len = reinterpret_cast<const int*>(h_pin_len.p);
   h_frm_len.assign(p_len, p_len + B);
   h_frm_off.assign(p_len + B, p_len + 2 * B + 1);
-  Tfrm = h_frm_off[B];
-  maxFrm = 0;
-  for (int b = 0; b < B; ++b) maxFrm = std::max(maxFrm, h_frm_len[b]);
+  set_frame_shape();
   have_durations = true;
 }
 
@@ -1480,11 +1566,12 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
   const int* fo = d_frm_off.p;
   if (!capturing) CK(cudaEventRecord(ev[4], stream));
   if (noise_z && !noise_on_device) {
-    // host noise was staged into h_pin_z by the caller (vtts_synthesize)
-    const size_t n = (size_t)B * I * z_ld;
+    // host noise was staged into h_pin_z by the caller (stage_noise_z) as [B][I][maxFrm]: the layout depends on the bucket only
+    const size_t n = (size_t)B * I * maxFrm;
     float* de = ensure(d_eps_z, n);
     CK(cudaMemcpyAsync(de, h_pin_z.p, n * sizeof(float), cudaMemcpyHostToDevice, stream));
     noise_z = de;
+    z_ld = maxFrm;
   }
   float* z = ensure(d_z, F * I);
   int* ftok = ensure(d_ftok, F);
@@ -1742,8 +1829,8 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
     mx = std::max(mx, (int)lengths[b]);
   }
   h->h_tok_off[B] = off;
-  h->Ttok = off;
-  h->maxTok = mx;
+  (void)mx;
+  h->set_token_shape();
   h->have_durations = false;
   h->have_latent = false;
 }
@@ -1759,15 +1846,16 @@ static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* len
   h->seed = seed;
   std::vector<int> packed(h->Ttok), sid32(B);
   for (int b = 0; b < B; ++b) {
-    for (int t = 0; t < h->h_tok_len[b]; ++t) packed[h->h_tok_off[b] + t] = (int)ids[(size_t)b * t_max + t];
+    for (int t = 0; t < h->h_tok_len[b]; ++t) {
+      const int64_t id = ids[(size_t)b * t_max + t];
+      REQUIRE(id >= 0 && id < h->cfg.n_vocab, VTTS_ERR_INVALID, "phoneme id out of range [0, n_vocab)");
+      packed[h->h_tok_off[b] + t] = (int)id;
+    }
+    REQUIRE(!h->has_g || (sid[b] >= 0 && sid[b] < h->cfg.n_speakers), VTTS_ERR_INVALID, "speaker id out of range [0, n_speakers)");
     sid32[b] = (int)sid[b];
   }
   h->stage1(packed.data(), sid32.data(), t_max, noise_dp);
-  uint64_t key = vtts_engine::mix(0x11, (uint64_t)B);
-  key = vtts_engine::mix(key, (uint64_t)t_max);
-  key = vtts_engine::mix(key, noise_dp ? 1 : 0);
-  for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
-  h->run_graphed(key, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
+  h->run_graphed({0x11, B, h->maxTok, h->Ttok, noise_dp ? 1 : 0}, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
   h->finish1();
   for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
   if (durations) {
@@ -1783,25 +1871,18 @@ static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* len
 
 static void impl_synthesize(vtts_handle h, const float* noise_z, int z_ld, float* wav, int64_t wav_ld, int32_t* frame_token, int idx_ld) {
   REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize called without vtts_durations");
-  REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
-  REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-  REQUIRE(!frame_token || idx_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
-  if (noise_z) {
-    const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
-    char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));   // caller memory may be pageable
-    memcpy(pin, noise_z, n * sizeof(float));
-  }
-  uint64_t key = vtts_engine::mix(0x22, (uint64_t)h->B);
-  key = vtts_engine::mix(key, (uint64_t)z_ld);
-  key = vtts_engine::mix(key, noise_z ? 1 : 0);
-  for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
-  h->run_graphed(key, [&] { h->phase2(noise_z, z_ld, false); });
-  const size_t nw = (size_t)h->Tfrm * h->hop;
-  char* pin = h->ensure_pinned(nw * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
+  REQUIRE((int64_t)h->real_maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+  REQUIRE(!noise_z || z_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+  REQUIRE(!frame_token || idx_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
+  if (noise_z) h->stage_noise_z(noise_z, z_ld);
+  // graph key = the length BUCKETS (token rows, frame rows), not the lengths: kernels read the true lengths on the device
+  h->run_graphed({0x22, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
+  const size_t nw = (size_t)h->real_Tfrm * h->hop;
+  char* pin = h->ensure_pinned((size_t)h->Tfrm * h->hop * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
   float* pw = reinterpret_cast<float*>(pin);
-  int* pi = reinterpret_cast<int*>(pw + nw);
+  int* pi = reinterpret_cast<int*>(pw + (size_t)h->Tfrm * h->hop);
   CK(cudaMemcpyAsync(pw, h->d_wav.p, nw * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-  if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)h->Tfrm * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)h->real_Tfrm * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaEventRecord(h->ev[7], h->stream));
   CK(cudaStreamSynchronize(h->stream));
   for (int b = 0; b < h->B; ++b) {
@@ -1818,26 +1899,18 @@ static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_
   memcpy(h->scales, scales, 3 * sizeof(float));
   h->seed = seed;
   h->stage1(nullptr, nullptr, t_max, nullptr);
-  uint64_t key = vtts_engine::mix(0x33, (uint64_t)B);
-  key = vtts_engine::mix(key, (uint64_t)t_max);
-  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_ids);
-  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_sid);
-  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_dp);
-  for (int b = 0; b < B; ++b) key = vtts_engine::mix(key, (uint64_t)h->h_tok_len[b]);
-  h->run_graphed(key, [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
+  h->eps_dp_ld = t_max;      // device noise is read in the caller's [B][2][t_max] layout
+  h->run_graphed({0x33, B, h->maxTok, h->Ttok, t_max, (long long)(uintptr_t)d_ids, (long long)(uintptr_t)d_sid, (long long)(uintptr_t)d_noise_dp},
+                 [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
   h->finish1();
   for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
 }
 
 static void impl_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
   REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize_dev called without vtts_durations_dev");
-  REQUIRE((int64_t)h->maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
-  REQUIRE(!d_noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-  uint64_t key = vtts_engine::mix(0x44, (uint64_t)h->B);
-  key = vtts_engine::mix(key, (uint64_t)z_ld);
-  key = vtts_engine::mix(key, (uint64_t)(uintptr_t)d_noise_z);
-  for (int b = 0; b < h->B; ++b) key = vtts_engine::mix(key, ((uint64_t)h->h_tok_len[b] << 32) | (uint64_t)h->h_frm_len[b]);
-  h->run_graphed(key, [&] { h->phase2(d_noise_z, z_ld, true); });
+  REQUIRE((int64_t)h->real_maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+  REQUIRE(!d_noise_z || z_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+  h->run_graphed({0x44, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
   for (int b = 0; b < h->B; ++b)
     CK(cudaMemcpyAsync(d_wav + (size_t)b * wav_ld, h->d_wav.p + (size_t)h->h_frm_off[b] * h->hop,
                        (size_t)h->h_frm_len[b] * h->hop * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -1924,6 +1997,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
+    if (const char* e = getenv("VTTS_BUCKETS")) h->use_buckets = atoi(e) != 0;    // 0: size everything by the exact lengths
     if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
     h->build_prefetch_list();
@@ -1970,6 +2044,8 @@ void vtts_destroy(vtts_handle h) {
   for (auto& kv : h->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   fr(h->d_prm.p);
   fr(h->d_pref.p);
+  fr(h->d_chunk.p);
+  fr(h->d_zp_dbg.p);
   if (h->h_map) cudaFreeHost(h->h_map);
   for (auto& e : h->ev) if (e) cudaEventDestroy(e);
   for (auto& e : h->prof_ev) if (e) cudaEventDestroy(e);
@@ -2013,12 +2089,8 @@ int vtts_decoder_halo(vtts_handle h) { return h ? 24 : 0; }
 int vtts_flow(vtts_handle h, const float* noise_z, int z_ld) {
   return guarded(h, [&] {
     REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_flow called without vtts_durations");
-    REQUIRE(!noise_z || z_ld >= h->maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-    if (noise_z) {
-      const size_t n = (size_t)h->B * h->cfg.inter_channels * z_ld;
-      char* pin = h->ensure_pinned(h->h_pin_z, n * sizeof(float));
-      memcpy(pin, noise_z, n * sizeof(float));
-    }
+    REQUIRE(!noise_z || z_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+    if (noise_z) h->stage_noise_z(noise_z, z_ld);
     h->last_graphed = false;
     h->phase2(noise_z, z_ld, false, /*run_decoder=*/false);
     CK(cudaStreamSynchronize(h->stream));
@@ -2042,19 +2114,21 @@ int vtts_decode_chunk(vtts_handle h, int f0, int f1, float* wav, int64_t wav_cap
     pin[0] = hi - lo; pin[1] = lo; pin[2] = hi;
     CK(cudaMemcpyAsync(dc, pin, 3 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     // the launch helpers size grids and split-K from the host copies of the lengths: point them at the chunk
-    const std::vector<int> len0 = h->h_frm_len, off0 = h->h_frm_off;
+    // (the planes keep the full utterance's row count, Tfrm: the chunk is addressed by its absolute rows)
+    const std::vector<int> len0 = h->h_frm_len, off0 = h->h_frm_off, v0 = h->v_frm_len;
     const int max0 = h->maxFrm;
     h->h_frm_len.assign(1, hi - lo);
     h->h_frm_off = {lo, hi};
+    h->v_frm_len = h->h_frm_len;
     h->maxFrm = hi - lo;
     try {
       h->last_graphed = false;
       h->decode(h->d_z.p, dc, dc + 1);
     } catch (...) {
-      h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0;
+      h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0; h->v_frm_len = v0;
       throw;
     }
-    h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0;
+    h->h_frm_len = len0; h->h_frm_off = off0; h->maxFrm = max0; h->v_frm_len = v0;
     const size_t n = (size_t)(f1 - f0) * h->hop;
     float* pw = reinterpret_cast<float*>(h->ensure_pinned(n * sizeof(float)));
     CK(cudaMemcpyAsync(pw, h->d_wav.p + (size_t)f0 * h->hop, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -2163,7 +2237,7 @@ int vtts_debug_read(vtts_handle h, const char* name, float* out, size_t max_floa
     const std::string nm(name);
     const float* src = nullptr;
     size_t n = 0;
-    const size_t T = h->Ttok, F = h->Tfrm;
+    const size_t T = h->real_Ttok, F = h->real_Tfrm;
     if (nm == "x") { src = h->d_x.p; n = T * c.hidden_channels; }
     else if (nm == "stats") { src = h->d_stats.p; n = T * 2 * c.inter_channels; }
     else if (nm == "dx") { src = h->d_dx.p; n = T * c.dp_filter_channels; }
@@ -2210,8 +2284,8 @@ int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host
     REQUIRE(L != nullptr, VTTS_ERR_INVALID, "layer must be enc.<i> or flow.<f>.tr");
     const int H = h->cfg.hidden_channels;
     REQUIRE(!use_tc || h->attn_tc_ok(*L, H), VTTS_ERR_INVALID, "tensor-core attention is not available for this layer / precision mode");
-    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len; const int mf0 = h->maxFrm;
-    h->B = 1; h->h_frm_len.assign(1, T); h->h_tok_len.assign(1, T); h->maxFrm = T;
+    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len, vf0 = h->v_frm_len, vt0 = h->v_tok_len; const int mf0 = h->maxFrm;
+    h->B = 1; h->h_frm_len.assign(1, T); h->h_tok_len.assign(1, T); h->maxFrm = T; h->v_frm_len = h->h_frm_len; h->v_tok_len = h->h_tok_len;
     int* dl = nullptr; float *dq = nullptr, *dout = nullptr;
     CK(cudaMalloc(&dl, 16));
     const int hl[3] = {T, 0, T};
@@ -2221,7 +2295,9 @@ int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host
     CK(cudaMemset(dout, 0, (size_t)T * H * 4));
     Planes pq;
     if (use_tc) {
-      pq = h->planes(58, T, 3 * H, false);
+      h->begin_planes();
+      pq = h->planes(58, T, 1, 3 * H);
+      h->flush_tails(dl, dl + 1);
       h->klaunch(split_planes_kernel, dim3(T, 1), dim3(64), (size_t)0, (const float*)dq, 3 * H, pq.hi, pq.lo, 3 * H, 3 * H, 1.f, 0, 1, (const int*)dl, (const int*)(dl + 1));
     }
     auto once = [&] {
@@ -2244,7 +2320,7 @@ int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
     cudaFree(dl); cudaFree(dq); cudaFree(dout);
-    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0; h->maxFrm = mf0;
+    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0; h->maxFrm = mf0; h->v_frm_len = vf0; h->v_tok_len = vt0;
   });
 }
 
@@ -2281,8 +2357,8 @@ float vtts_microbench(vtts_handle h, const char* what, int iters) {
     REQUIRE(is_tc || strcmp(kind, "ffma") == 0, VTTS_ERR_INVALID, "unknown microbench kind");
     REQUIRE(!is_tc || h->tc, VTTS_ERR_INVALID, "tc microbench needs a precision-1 engine");
     // save state that the launch helpers read
-    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len;
-    h->B = 1; h->h_frm_len.assign(1, rows); h->h_tok_len.assign(1, rows);
+    const int B0 = h->B; const std::vector<int> fl0 = h->h_frm_len, tl0 = h->h_tok_len, vf0 = h->v_frm_len, vt0 = h->v_tok_len;
+    h->B = 1; h->h_frm_len.assign(1, rows); h->h_tok_len.assign(1, rows); h->v_frm_len = h->h_frm_len; h->v_tok_len = h->h_tok_len;
     int* dl = nullptr; int* dof = nullptr; float *x = nullptr, *y = nullptr, *w = nullptr, *bias = nullptr;
     __nv_bfloat16 *ph = nullptr, *pl = nullptr, *wh = nullptr, *wl = nullptr;
     const int ldw = (Cout + 3) / 4 * 4;
@@ -2352,7 +2428,7 @@ float vtts_microbench(vtts_handle h, const char* what, int iters) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     h->profiling = prof0;
     for (void* p2 : {(void*)dl, (void*)dof, (void*)x, (void*)y, (void*)w, (void*)bias, (void*)ph, (void*)pl, (void*)wh, (void*)wl}) if (p2) cudaFree(p2);
-    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0;
+    h->B = B0; h->h_frm_len = fl0; h->h_tok_len = tl0; h->v_frm_len = vf0; h->v_tok_len = vt0;
   });
   return rc == VTTS_OK ? result : (float)rc;
 }

@@ -453,7 +453,7 @@ __global__ void cond_kernel(const float* __restrict__ emb_g, const int* __restri
   extern __shared__ float gs[];
   const int b = blockIdx.y;
   int s = sid[b];
-  s = s < 0 ? 0 : (s >= n_speakers ? n_speakers - 1 : s);
+  s = s < 0 ? 0 : (s >= n_speakers ? n_speakers - 1 : s);      // memory-safety net for the *_dev entry points only: the host path rejects out-of-range ids
   for (int i = threadIdx.x; i < G; i += blockDim.x) gs[i] = emb_g[(long)s * G + i];
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1315,6 +1315,35 @@ __global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restri
       host_out[0] = __float_as_int(prm[6]);
     }
   }
+}
+
+// Split-bf16 planes are read by TMA with a conv halo (and, in the attention, whole key tiles) that reaches past the end of
+// an utterance.  Rows outside [0, len) are never written by any producer, but the buffers are reused by calls with other
+// lengths, so the rows right behind every utterance of THIS call's layout may hold a previous call's data: they are zeroed
+// here, once per phase, for every plane buffer the phase uses (up to ZT_ROWS rows or up to the next utterance's first row;
+// the largest halo of the path is 25 rows at >= 4x upsampling where the inter-utterance gap is >= 32 rows, and <= 3 rows at
+// frame/token resolution where the gap is SEQ_GAP = 8).  Rows beyond the tensor map's row count read as zero through TMA's
+// out-of-bounds fill.  This replaces per-call memsets of whole planes and lets captured graphs serve any length in a bucket.
+constexpr int ZT_ROWS = 32, ZT_MAXP = 56;
+struct TailList {
+  struct E { __nv_bfloat16* hi; __nv_bfloat16* lo; int C, rm, extra, rows_cap; } e[ZT_MAXP];
+  int n;
+};
+__global__ void zero_tails_kernel(const __grid_constant__ TailList tl, const int* __restrict__ lens, const int* __restrict__ offs, int B) {
+  PDL_LAUNCH();
+  PDL_WAIT();
+  const TailList::E& e = tl.e[blockIdx.x];
+  const int b = blockIdx.y;
+  const long start = ((long)offs[b] + lens[b]) * e.rm + (long)(b + 1) * e.extra;
+  long stop = start + ZT_ROWS;
+  if (b + 1 < B) stop = min(stop, (long)offs[b + 1] * e.rm + (long)(b + 1) * e.extra);
+  stop = min(stop, (long)e.rows_cap);
+  const long n8 = (stop - start) * e.C / 8;          // C % 8 == 0: rows are 16-byte multiples
+  if (n8 <= 0) return;
+  uint4* ph = reinterpret_cast<uint4*>(e.hi + start * e.C);
+  uint4* pl = reinterpret_cast<uint4*>(e.lo + start * e.C);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  for (long i = threadIdx.x; i < n8; i += blockDim.x) { ph[i] = z; pl[i] = z; }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -180,6 +180,14 @@ class Engine:
         self.hop = self.lib.vtts_hop(self.h)
         self.device = device
 
+    def _out_buffer(self, B, n):
+        """Scratch output rows reused across calls (callers hold the session lock); row pitch = buf.shape[1] >= n."""
+        buf = getattr(self, "_wav_buf", None)
+        if buf is None or buf.shape[0] < B or buf.shape[1] < n:
+            buf = np.empty((B, n), np.float32)
+            self._wav_buf = buf
+        return buf[:B]
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.vtts_destroy(self.h)
@@ -245,7 +253,7 @@ class Engine:
                 noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
                 z_ld = noise_z.shape[2]
             y_len = np.zeros(B, np.int64)
-            wav = np.zeros((B, int(frames_hint) * self.hop), np.float32)
+            wav = self._out_buffer(B, int(frames_hint) * self.hop)       # reused across calls; the engine writes y_len*hop samples per row
             rc = self.lib.vtts_infer(self.h, _ptr(ids), _ptr(lengths), _ptr(sid), B, t_max, _ptr(scales), _ptr(noise_dp),
                                      _ptr(noise_z), z_ld, int(seed), _ptr(y_len), _ptr(wav), wav.shape[1], None, 0)
             self._B = B
@@ -254,7 +262,12 @@ class Engine:
                     self._check(rc)
                 return self.synthesize(y_len, noise_z), y_len
             self._check(rc)
-            return wav[:, : int(y_len.max()) * self.hop], y_len
+            n = int(y_len.max()) * self.hop
+            out = np.zeros((B, n), np.float32)                           # contiguous result sized to max(y_len); rows are zero beyond their length
+            for b in range(B):
+                m = int(y_len[b]) * self.hop
+                out[b, :m] = wav[b, :m]
+            return out, y_len
         y_len = self.durations(ids, lengths, sid, scales, noise_dp, seed)
         if callable(noise_z):
             noise_z = noise_z(int(y_len.max()))
