@@ -141,6 +141,10 @@ float vtts_microbench(vtts_handle h, const char* what, int iters);
  * the ~160 per-call kernel-launch overheads at batch 1.  vtts_graph_replays counts graph launches so far. */
 int vtts_set_graphs(vtts_handle h, int enable);
 uint64_t vtts_graph_replays(vtts_handle h);
+/* Single-utterance vtts_infer / vtts_infer_dev calls enqueue the second phase for a PREDICTED length bucket without waiting
+ * for the durations (the kernels read the true lengths on the device) and repeat it only when the prediction was too small:
+ * hits / misses since creation. */
+int vtts_speculation_stats(vtts_handle h, uint64_t* hits, uint64_t* misses);
 
 /* Per-launch profiling of the dense-conv kernel family (the dominant kernels): while enabled every launch is
  * bracketed by CUDA events on the engine's stream.  vtts_profile_read returns the summed device time, the

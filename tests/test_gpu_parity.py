@@ -177,14 +177,106 @@ def test_graph_replay_equals_eager(engine, cfg):
     assert engine.graph_replays() > n0
 
 
+def test_one_handle_called_from_several_threads(engine, cfg):
+    """The gRPC server of the reference calls ONE shared session from a thread pool (server/tts_server.py:35,57).  Both the
+    one-shot call (vtts_infer) and the two-phase pair (vtts_durations -> vtts_synthesize, which keeps state in the handle
+    between the calls) must give every thread its own utterance's result."""
+    import threading
+    g = torch.Generator().manual_seed(5)
+    jobs = []
+    for i in range(6):
+        T = int(torch.randint(20, 90, (1,), generator=g))
+        jobs.append((torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy(), T, i % 5,
+                     torch.randn(1, 2, T, generator=g).numpy(), torch.randn(1, 192, 12 * T, generator=g).numpy()))
+    serial = []
+    for tok, T, sid, e1, e2 in jobs:
+        yl = engine.durations(tok, [T], [sid], (0.8, 1.0, 0.8), e1)
+        serial.append(engine.synthesize(yl, e2[:, :, : int(yl[0])]).copy())
+    out, errs = [None] * len(jobs), []
+
+    def work(k, two_phase):
+        try:
+            for rep in range(4):
+                tok, T, sid, e1, e2 = jobs[k]
+                if two_phase:
+                    yl = engine.lib_durations_threadsafe(tok, [T], [sid], (0.8, 1.0, 0.8), e1)
+                    w = engine.lib_synthesize_threadsafe(1, yl, e2[:, :, : int(yl[0])])
+                else:
+                    w, yl = engine.infer(tok, [T], [sid], (0.8, 1.0, 0.8), e1, e2[:, :, : serial[k].shape[1] // 256], frames_hint=serial[k].shape[1] // 256)
+                out[k] = np.array(w)
+        except Exception as ex:      # noqa: BLE001
+            errs.append(repr(ex))
+
+    th = [threading.Thread(target=work, args=(k, k % 2 == 0)) for k in range(len(jobs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for k in range(len(jobs)):
+        assert out[k].shape == serial[k].shape and np.array_equal(out[k], serial[k]), "thread %d got another utterance's result" % k
+
+
+def test_speculative_second_phase_hits_and_misses(engine, cfg):
+    """Single-utterance infer calls enqueue phase 2 for a predicted length bucket before the durations are known.  Whatever
+    the prediction, the result must equal the two-phase API's; a call whose frame count exceeds the prediction (here: a
+    much smaller length_scale after a run of normal ones, so that the one-frame-per-token floor dominates) is repeated."""
+    g = torch.Generator().manual_seed(91)
+    h0, m0 = engine.speculation_stats()
+    plan = [(100, 1.0), (90, 1.0), (110, 1.1), (100, 0.25), (96, 1.0), (100, 2.0), (64, 1.0)]
+    for T, ls in plan:
+        tok = torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy()
+        eps_dp = torch.randn(1, 2, T, generator=g).numpy()
+        scales = (0.8, ls, 0.8)
+        yl = engine.durations(tok, [T], [1], scales, eps_dp)
+        Ty = int(yl[0])
+        eps_z = torch.randn(1, 192, Ty, generator=g).numpy()
+        ref = engine.synthesize(yl, eps_z)
+        wav, yl2 = engine.infer(tok, [T], [1], scales, eps_dp, eps_z, frames_hint=Ty + 40)
+        assert int(yl2[0]) == Ty
+        assert np.array_equal(wav[:, : Ty * 256], ref[:, : Ty * 256])
+    h1, m1 = engine.speculation_stats()
+    assert h1 - h0 >= 4 and m1 - m0 >= 1, (h1 - h0, m1 - m0)
+
+
+def test_bucketed_graphs_serve_unseen_utterances(engine, cfg):
+    """Graphs are captured per LENGTH BUCKET: utterances that were never seen before (other tokens, other lengths inside the
+    bucket, other noise) must replay a captured graph and give exactly what eager launches give -- including a short
+    utterance right after a longer one of the same bucket (rows behind the utterance's end hold the previous call's data
+    until zero_tails_kernel clears them)."""
+    g = torch.Generator().manual_seed(77)
+    cases = []
+    for T in (128, 121, 113, 126, 115, 128, 119):                       # one token bucket (113..128)
+        tok = torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy()
+        eps_dp = torch.randn(1, 2, T, generator=g).numpy()
+        eps_z = torch.randn(1, 192, 12 * T, generator=g).numpy()
+        cases.append((tok, T, eps_dp, eps_z))
+    engine.set_graphs(False)
+    refs = []
+    for tok, T, eps_dp, eps_z in cases:
+        yl = engine.durations(tok, [T], [3], (0.8, 1.0, 0.8), eps_dp)
+        refs.append((int(yl[0]), engine.synthesize(yl, eps_z[:, :, : int(yl[0])]).copy()))
+    engine.set_graphs(True)
+    n0 = engine.graph_replays()
+    for rep in range(3):
+        for (tok, T, eps_dp, eps_z), (Ty, ref) in zip(cases, refs):
+            yl = engine.durations(tok, [T], [3], (0.8, 1.0, 0.8), eps_dp)
+            assert int(yl[0]) == Ty
+            wav = engine.synthesize(yl, eps_z[:, :, :Ty])
+            assert np.array_equal(wav, ref), "graph replay differs from eager launches (rep %d, T=%d)" % (rep, T)
+    # after the buckets have been seen twice everything replays: 7 utterances x 2 phases in the last repetition alone
+    assert engine.graph_replays() - n0 >= 14
+
+
 @pytest.mark.parametrize("env", [{"VTTS_TC_BN": "128"}, {"VTTS_TC_TALL": "1"}, {"VTTS_PDL": "0"}, {"VTTS_CONV_MAXS": "1", "VTTS_CONV_MAXG": "4"},
                                  {"VTTS_ATTN_ROWS": "4"}, {"VTTS_TC_MULTICAST": "1"}, {"VTTS_TC_SPLIT": "1"}, {"VTTS_TC_SPLIT": "2"},
                                  {"VTTS_TC_MINSTEPS": "1"}, {"VTTS_TC_BN": "128", "VTTS_TC_MINSTEPS": "1"}, {"VTTS_TC_BN": "64"}, {"VTTS_ATTN_SPLIT": "0"},
-                                 {"VTTS_CONV_AUTOG": "0"}, {"VTTS_MRF_BRANCH": "1"}],
+                                 {"VTTS_CONV_AUTOG": "0"}, {"VTTS_MRF_BRANCH": "1"}, {"VTTS_BUCKETS": "0"}, {"VTTS_ATTN_TC": "0"}],
                          ids=["tc-128-wide-tiles", "tc-tall-activation-tiles", "no-programmatic-dependent-launch", "ffma-no-cluster-4-groups",
                               "attention-4-rows-per-warp", "tc-tma-multicast-cluster", "tc-no-split-k", "tc-split-k-pairs",
                               "tc-split-k-8-ways", "tc-128-wide-split-k-8-ways", "tc-64-wide-only", "attention-without-split-kv",
-                              "ffma-single-thread-group", "mrf-chains-on-separate-streams"])
+                              "ffma-single-thread-group", "mrf-chains-on-separate-streams", "exact-sizes-no-length-buckets",
+                              "ffma-attention-in-the-flow"])
 def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
     """The tuning switches select different tilings / launch modes of the same kernels (128-wide tcgen05 tiles are what
     batched calls use automatically); each must still reproduce the reference fixture."""

@@ -10,6 +10,9 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <thread>
 #include <initializer_list>
 #include <map>
 #include <mutex>
@@ -135,6 +138,12 @@ struct vtts_engine {
   int device = 0;
   cudaStream_t stream = nullptr;
   std::mutex mu;
+  // The two-phase API (vtts_durations -> vtts_synthesize / vtts_flow) keeps per-handle state between two calls.  A thread
+  // that has run vtts_durations owns the handle until its vtts_synthesize / vtts_flow has succeeded (or failed for good);
+  // entry points called by OTHER threads wait for that instead of overwriting the pending durations.
+  bool two_phase = false;
+  std::thread::id owner;
+  std::condition_variable cv;
   std::string err;
   uint64_t launches = 0;
 
@@ -179,6 +188,36 @@ struct vtts_engine {
   int real_Ttok = 0, real_maxTok = 0, real_Tfrm = 0, real_maxFrm = 0;
   std::vector<int> v_tok_len, v_frm_len;
   bool use_buckets = true;
+  // Speculative second phase (single utterances): the frame count is data dependent, but the kernels read it from device
+  // memory and the host only needs an upper bound -- the length bucket -- to size grids and pick the graph.  The bound is
+  // predicted from the frames-per-(token x length_scale) ratio of recent calls, phase 2 is enqueued for that bucket right
+  // behind phase 1 WITHOUT the host waiting for the lengths, and repeated with the right bucket in the rare case the
+  // prediction was too small.  A whole utterance is then two graph launches and one synchronisation; the phase-1 ->
+  // host -> phase-2 round trip (~50 us, and the part of a step most exposed to host jitter) is gone.
+  bool use_spec = true;
+  float spec_hist[16] = {};
+  int spec_n = 0;
+  float spec_ratio = 0.f;
+  uint64_t spec_hits = 0, spec_misses = 0;
+  double spec_units() const { return (double)real_maxTok * (double)std::max(0.05f, scales[1]); }
+  int spec_predict() const { return (int)std::ceil((double)spec_ratio * 1.04 * spec_units()) + 4; }
+  void spec_learn() {
+    spec_hist[spec_n++ % 16] = (float)((double)real_maxFrm / spec_units());
+    float m = 0.f;
+    for (int i = 0; i < std::min(spec_n, 16); ++i) m = std::max(m, spec_hist[i]);
+    spec_ratio = m;
+  }
+  void assume_frames(int frames) {      // host-side frame shape from a prediction (B == 1)
+    h_frm_len.assign(1, frames);
+    h_frm_off = {0, frames};
+    set_frame_shape();
+  }
+  bool read_published_lengths() {       // what frame_offsets_kernel wrote into mapped host memory; false: not there (yet)
+    if (!h_map || h_map[0] != call_seq) return false;
+    h_frm_len.assign(h_map + 1, h_map + 1 + B);
+    h_frm_off.assign(h_map + 1 + B, h_map + 1 + 2 * B + 1);
+    return true;
+  }
   int eps_dp_ld = 0;                 // row pitch of the duration-predictor noise the phase-1 kernels read
   static int bucket_tok(int n) { return n <= 256 ? (n + 15) / 16 * 16 : (n + 63) / 64 * 64; }
   static int bucket_frm(int n) { return n <= 512 ? (n + 31) / 32 * 32 : (n <= 4096 ? (n + 127) / 128 * 128 : (n + 511) / 512 * 512); }
@@ -1780,21 +1819,41 @@ void vtts_engine::decode(float* z, const int* fl, const int* fo) {
 // ===================================================================================================
 namespace {
 
+enum : int { G_ATOMIC = 0, G_BEGIN = 1, G_CONT = 2 };    // one-shot call | opens a two-phase section | continues / closes it
+
 template <typename Fn>
-int guarded(vtts_handle h, Fn fn) {
+int guarded(vtts_handle h, Fn fn, int mode = G_ATOMIC) {
   if (!h) return VTTS_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(h->mu);
+  std::unique_lock<std::mutex> lk(h->mu);
+  const std::thread::id me = std::this_thread::get_id();
+  if (mode == G_CONT) {
+    if (!h->two_phase || h->owner != me) {
+      h->err = "second phase called without a preceding vtts_durations by the same thread";
+      return VTTS_ERR_STATE;
+    }
+  } else if (h->two_phase && h->owner != me) {
+    if (!h->cv.wait_for(lk, std::chrono::seconds(60), [&] { return !h->two_phase; })) {
+      h->err = "another thread has held this handle between vtts_durations and vtts_synthesize for 60 s";
+      return VTTS_ERR_STATE;
+    }
+  }
+  auto close = [&] { if (h->two_phase) { h->two_phase = false; h->cv.notify_all(); } };
+  if (mode != G_CONT) close();          // (the owner itself starting over)
   try {
     cudaError_t e = cudaSetDevice(h->device);
     if (e != cudaSuccess) throw Err{VTTS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
     fn();
+    if (mode == G_BEGIN) { h->two_phase = true; h->owner = me; }
+    if (mode == G_CONT) close();
     return VTTS_OK;
   } catch (const Err& e) {
     h->err = e.msg;
     cudaGetLastError();
+    if (mode == G_CONT && e.code != VTTS_ERR_CAPACITY) close();     // a capacity error keeps the durations for a retry
     return e.code;
   } catch (const std::exception& e) {
     h->err = e.what();
+    if (mode == G_CONT) close();
     return VTTS_ERR_INVALID;
   }
 }
@@ -1839,8 +1898,8 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
 
 namespace {
 
-static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
-                   const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
+static void enqueue_phase1_host(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
+                               const float* scales, const float* noise_dp, uint64_t seed) {
   setup_lengths(h, lengths, B, t_max);
   memcpy(h->scales, scales, 3 * sizeof(float));
   h->seed = seed;
@@ -1856,7 +1915,13 @@ static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* len
   }
   h->stage1(packed.data(), sid32.data(), t_max, noise_dp);
   h->run_graphed({0x11, B, h->maxTok, h->Ttok, noise_dp ? 1 : 0}, [&] { h->phase1(packed.data(), nullptr, t_max, nullptr, sid32.data(), noise_dp, false); });
+}
+
+static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
+                   const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
+  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed);
   h->finish1();
+  if (B == 1) h->spec_learn();
   for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
   if (durations) {
     std::vector<int> wc(h->Ttok);
@@ -1893,8 +1958,8 @@ static void impl_synthesize(vtts_handle h, const float* noise_z, int z_ld, float
   h->have_durations = false;
 }
 
-static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
-                       const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
+static void enqueue_phase1_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                              const float* scales, const float* d_noise_dp, uint64_t seed) {
   setup_lengths(h, lengths_host, B, t_max);
   memcpy(h->scales, scales, 3 * sizeof(float));
   h->seed = seed;
@@ -1902,8 +1967,107 @@ static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_
   h->eps_dp_ld = t_max;      // device noise is read in the caller's [B][2][t_max] layout
   h->run_graphed({0x33, B, h->maxTok, h->Ttok, t_max, (long long)(uintptr_t)d_ids, (long long)(uintptr_t)d_sid, (long long)(uintptr_t)d_noise_dp},
                  [&] { h->phase1(nullptr, d_ids, t_max, d_sid, nullptr, d_noise_dp, true); });
+}
+
+static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                       const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
+  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed);
   h->finish1();
+  if (B == 1) h->spec_learn();
   for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
+}
+
+static void impl_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld);
+
+static bool spec_ok(vtts_handle h, int B) {
+  return B == 1 && h->use_spec && h->use_poll && h->spec_ratio > 0.f && !h->profiling && !h->debug_flags;
+}
+
+// Both phases of one call through host buffers (vtts_infer).
+static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max, const float* scales,
+                       const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed, int64_t* y_lengths, float* wav, int64_t wav_ld,
+                       int32_t* frame_token, int idx_ld, int* phase) {
+  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed);
+  if (spec_ok(h, B)) {
+    h->assume_frames(h->spec_predict());
+    const int cap = h->maxFrm;
+    if (noise_z) h->stage_noise_z(noise_z, z_ld);
+    h->run_graphed({0x22, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
+    // the true length is not known on the host yet: the bucket's worth of samples comes back
+    const size_t ncap = (size_t)cap * h->hop;
+    char* pin = h->ensure_pinned(ncap * sizeof(float) + (size_t)cap * sizeof(int) + 64);
+    float* pw = reinterpret_cast<float*>(pin);
+    int* pi = reinterpret_cast<int*>(pw + ncap);
+    CK(cudaMemcpyAsync(pw, h->d_wav.p, ncap * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)cap * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    REQUIRE(h->read_published_lengths(), VTTS_ERR_CUDA, "phase 1 finished without publishing the utterance lengths");
+    const int real = h->h_frm_len[0];
+    h->real_Tfrm = real; h->real_maxFrm = real;
+    h->spec_learn();
+    y_lengths[0] = real;
+    *phase = 1;
+    if (real <= cap) {
+      ++h->spec_hits;
+      h->last_graphed = true;
+      h->have_durations = true;          // (kept if one of the capacity checks below fails)
+      REQUIRE((int64_t)real * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+      REQUIRE(!noise_z || z_ld >= real, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+      REQUIRE(!frame_token || idx_ld >= real, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
+      memcpy(wav, pw, (size_t)real * h->hop * sizeof(float));
+      if (frame_token) memcpy(frame_token, pi, (size_t)real * sizeof(int));
+      h->have_durations = false;
+      return;
+    }
+    ++h->spec_misses;                    // predicted bucket too small: run the second phase again with the real shape
+    h->set_frame_shape();
+    h->have_durations = true;
+  } else {
+    h->finish1();
+    if (B == 1) h->spec_learn();
+    for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
+    *phase = 1;
+  }
+  impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld);
+}
+
+// Both phases through device buffers (vtts_infer_dev).
+static void impl_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
+                           const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
+                           int64_t* y_lengths_host, float* d_wav, int64_t wav_ld, int* phase) {
+  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed);
+  if (spec_ok(h, B)) {
+    h->assume_frames(h->spec_predict());
+    const int cap = h->maxFrm;
+    h->run_graphed({0x44, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
+    const size_t ncopy = (size_t)std::min<int64_t>((int64_t)cap * h->hop, wav_ld);
+    CK(cudaMemcpyAsync(d_wav, h->d_wav.p, ncopy * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    REQUIRE(h->read_published_lengths(), VTTS_ERR_CUDA, "phase 1 finished without publishing the utterance lengths");
+    const int real = h->h_frm_len[0];
+    h->real_Tfrm = real; h->real_maxFrm = real;
+    h->spec_learn();
+    y_lengths_host[0] = real;
+    *phase = 1;
+    if (real <= cap) {
+      ++h->spec_hits;
+      h->last_graphed = true;
+      h->have_durations = true;
+      REQUIRE((int64_t)real * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
+      REQUIRE(!d_noise_z || z_ld >= real, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
+      h->have_durations = false;
+      return;
+    }
+    ++h->spec_misses;
+    h->set_frame_shape();
+    h->have_durations = true;
+  } else {
+    h->finish1();
+    if (B == 1) h->spec_learn();
+    for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
+    *phase = 1;
+  }
+  impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld);
 }
 
 static void impl_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
@@ -1997,7 +2161,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
-    if (const char* e = getenv("VTTS_BUCKETS")) h->use_buckets = atoi(e) != 0;    // 0: size everything by the exact lengths
+    if (const char* e = getenv("VTTS_BUCKETS")) h->use_buckets = atoi(e) != 0;
+    if (const char* e = getenv("VTTS_SPEC")) h->use_spec = atoi(e) != 0;          // 0: never enqueue phase 2 before the lengths are known    // 0: size everything by the exact lengths
     if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
     h->build_prefetch_list();
@@ -2063,23 +2228,23 @@ const char* vtts_last_error(vtts_handle h) { return h ? h->err.c_str() : "null h
 int vtts_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
                    const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
   if (!ids || !lengths || !sid || !scales || !y_lengths) return VTTS_ERR_INVALID;
-  return guarded(h, [&] { impl_durations(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, y_lengths, durations); });
+  return guarded(h, [&] { impl_durations(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, y_lengths, durations); }, G_BEGIN);
 }
 
 int vtts_synthesize(vtts_handle h, const float* noise_z, int z_ld, float* wav, int64_t wav_ld, int32_t* frame_token, int idx_ld) {
   if (!wav) return VTTS_ERR_INVALID;
-  return guarded(h, [&] { impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld); });
+  return guarded(h, [&] { impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld); }, G_CONT);
 }
 
 int vtts_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
                        const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
   if (!d_ids || !lengths_host || !d_sid || !scales || !y_lengths_host) return VTTS_ERR_INVALID;
-  return guarded(h, [&] { impl_durations_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, y_lengths_host); });
+  return guarded(h, [&] { impl_durations_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, y_lengths_host); }, G_BEGIN);
 }
 
 int vtts_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld, float* d_wav, int64_t wav_ld) {
   if (!d_wav) return VTTS_ERR_INVALID;
-  return guarded(h, [&] { impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld); });
+  return guarded(h, [&] { impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld); }, G_CONT);
 }
 
 // ---- streaming: flow once, then decode halo-extended chunks (the decoder's receptive field is
@@ -2096,7 +2261,7 @@ int vtts_flow(vtts_handle h, const float* noise_z, int z_ld) {
     CK(cudaStreamSynchronize(h->stream));
     h->have_durations = false;
     h->have_latent = true;
-  });
+  }, G_CONT);
 }
 
 int vtts_decode_chunk(vtts_handle h, int f0, int f1, float* wav, int64_t wav_capacity) {
@@ -2141,20 +2306,32 @@ int vtts_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const 
                const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed, int64_t* y_lengths, float* wav, int64_t wav_ld,
                int32_t* frame_token, int idx_ld) {
   if (!ids || !lengths || !sid || !scales || !y_lengths || !wav) return VTTS_ERR_INVALID;
-  return guarded(h, [&] {
-    impl_durations(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, y_lengths, nullptr);
-    impl_synthesize(h, noise_z, z_ld, wav, wav_ld, frame_token, idx_ld);
+  int phase = 0;
+  const int rc = guarded(h, [&] {
+    impl_infer(h, ids, lengths, sid, B, t_max, scales, noise_dp, noise_z, z_ld, seed, y_lengths, wav, wav_ld, frame_token, idx_ld, &phase);
   });
+  if (rc == VTTS_ERR_CAPACITY && phase == 1) {      // durations are kept: this thread may finish with vtts_synthesize
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->two_phase = true;
+    h->owner = std::this_thread::get_id();
+  }
+  return rc;
 }
 
 int vtts_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
                    const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
                    int64_t* y_lengths_host, float* d_wav, int64_t wav_ld) {
   if (!d_ids || !lengths_host || !d_sid || !scales || !y_lengths_host || !d_wav) return VTTS_ERR_INVALID;
-  return guarded(h, [&] {
-    impl_durations_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, y_lengths_host);
-    impl_synthesize_dev(h, d_noise_z, z_ld, d_wav, wav_ld);
+  int phase = 0;
+  const int rc = guarded(h, [&] {
+    impl_infer_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, d_noise_z, z_ld, seed, y_lengths_host, d_wav, wav_ld, &phase);
   });
+  if (rc == VTTS_ERR_CAPACITY && phase == 1) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->two_phase = true;
+    h->owner = std::this_thread::get_id();
+  }
+  return rc;
 }
 
 int vtts_hop(vtts_handle h) { return h ? h->hop : 0; }
@@ -2173,6 +2350,13 @@ int vtts_set_graphs(vtts_handle h, int enable) {
 }
 
 uint64_t vtts_graph_replays(vtts_handle h) { return h ? h->graph_replays : 0; }
+
+int vtts_speculation_stats(vtts_handle h, uint64_t* hits, uint64_t* misses) {
+  if (!h || !hits || !misses) return VTTS_ERR_INVALID;
+  *hits = h->spec_hits;
+  *misses = h->spec_misses;
+  return VTTS_OK;
+}
 
 int vtts_profile(vtts_handle h, int enable) {
   return guarded(h, [&] {

@@ -43,7 +43,7 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
            "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev",
-           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention"]
+           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention", "vtts_speculation_stats"]
 
 
 def lib_path():
@@ -114,6 +114,8 @@ def load_library(build_if_missing=True):
     lib.vtts_profile_read_tc.restype = i32
     lib.vtts_debug_attention.argtypes = [vp, C.c_char_p, vp, i32, i32, vp, i32, fp]
     lib.vtts_debug_attention.restype = i32
+    lib.vtts_speculation_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.vtts_speculation_stats.restype = i32
     _LIB = lib
     return lib
 
@@ -180,14 +182,6 @@ class Engine:
         self.hop = self.lib.vtts_hop(self.h)
         self.device = device
 
-    def _out_buffer(self, B, n):
-        """Scratch output rows reused across calls (callers hold the session lock); row pitch = buf.shape[1] >= n."""
-        buf = getattr(self, "_wav_buf", None)
-        if buf is None or buf.shape[0] < B or buf.shape[1] < n:
-            buf = np.empty((B, n), np.float32)
-            self._wav_buf = buf
-        return buf[:B]
-
     def close(self):
         if getattr(self, "h", None):
             self.lib.vtts_destroy(self.h)
@@ -234,6 +228,30 @@ class Engine:
         self._check(self.lib.vtts_synthesize(self.h, _ptr(noise_z), z_ld, _ptr(wav), wav.shape[1], _ptr(idx), max_f))
         return (wav, idx) if want_alignment else wav
 
+    # Thread-safe variants of the two-phase pair: no per-Engine Python state (the batch size travels with the caller)
+    def lib_durations_threadsafe(self, ids, lengths, sid, scales, noise_dp=None, seed=0):
+        ids = np.ascontiguousarray(ids, dtype=np.int64)
+        B, t_max = ids.shape
+        lengths = np.ascontiguousarray(lengths, dtype=np.int64).reshape(B)
+        sid = np.ascontiguousarray(sid, dtype=np.int64).reshape(B)
+        scales = np.ascontiguousarray(scales, dtype=np.float32).reshape(3)
+        if noise_dp is not None:
+            noise_dp = np.ascontiguousarray(noise_dp, dtype=np.float32).reshape(B, 2, t_max)
+        y_len = np.zeros(B, np.int64)
+        self._check(self.lib.vtts_durations(self.h, _ptr(ids), _ptr(lengths), _ptr(sid), B, t_max, _ptr(scales), _ptr(noise_dp), int(seed),
+                                            _ptr(y_len), None))
+        return y_len
+
+    def lib_synthesize_threadsafe(self, B, y_lengths, noise_z=None):
+        max_f = int(np.max(y_lengths))
+        wav = np.zeros((B, max_f * self.hop), np.float32)
+        z_ld = 0
+        if noise_z is not None:
+            noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
+            z_ld = noise_z.shape[2]
+        self._check(self.lib.vtts_synthesize(self.h, _ptr(noise_z), z_ld, _ptr(wav), wav.shape[1], None, 0))
+        return wav
+
     def infer(self, ids, lengths, sid, scales, noise_dp=None, noise_z=None, seed=0, frames_hint=None):
         """Both phases.  noise_z may be a callable(max_frames)->[B,C,max_frames] (T_y is data dependent).
         With `frames_hint` (an upper bound on max(y_lengths), e.g. from a previous call) and array/None noise, the
@@ -253,7 +271,7 @@ class Engine:
                 noise_z = np.ascontiguousarray(noise_z, dtype=np.float32)
                 z_ld = noise_z.shape[2]
             y_len = np.zeros(B, np.int64)
-            wav = self._out_buffer(B, int(frames_hint) * self.hop)       # reused across calls; the engine writes y_len*hop samples per row
+            wav = np.empty((B, int(frames_hint) * self.hop), np.float32)   # (np.empty: no zero fill of the capacity-sized buffer; the engine writes y_len*hop samples per row)
             rc = self.lib.vtts_infer(self.h, _ptr(ids), _ptr(lengths), _ptr(sid), B, t_max, _ptr(scales), _ptr(noise_dp),
                                      _ptr(noise_z), z_ld, int(seed), _ptr(y_len), _ptr(wav), wav.shape[1], None, 0)
             self._B = B
@@ -350,6 +368,12 @@ class Engine:
 
     def graph_replays(self):
         return int(self.lib.vtts_graph_replays(self.h))
+
+    def speculation_stats(self):
+        """(hits, misses) of the speculative second phase of single-utterance infer calls."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.vtts_speculation_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
 
     def profile(self, enable):
         self._check(self.lib.vtts_profile(self.h, int(bool(enable))))
