@@ -186,12 +186,14 @@ def test_one_handle_called_from_several_threads(engine, cfg):
     jobs = []
     for i in range(6):
         T = int(torch.randint(20, 90, (1,), generator=g))
-        jobs.append((torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy(), T, i % 5,
-                     torch.randn(1, 2, T, generator=g).numpy(), torch.randn(1, 192, 12 * T, generator=g).numpy()))
+        jobs.append([torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy(), T, i % 5,
+                     torch.randn(1, 2, T, generator=g).numpy(), None])
     serial = []
-    for tok, T, sid, e1, e2 in jobs:
+    for job in jobs:
+        tok, T, sid, e1, _ = job
         yl = engine.durations(tok, [T], [sid], (0.8, 1.0, 0.8), e1)
-        serial.append(engine.synthesize(yl, e2[:, :, : int(yl[0])]).copy())
+        job[4] = torch.randn(1, 192, int(yl[0]), generator=g).numpy()       # (the frame count is data dependent)
+        serial.append(engine.synthesize(yl, job[4]).copy())
     out, errs = [None] * len(jobs), []
 
     def work(k, two_phase):
@@ -214,7 +216,9 @@ def test_one_handle_called_from_several_threads(engine, cfg):
         t.join()
     assert not errs, errs
     for k in range(len(jobs)):
-        assert out[k].shape == serial[k].shape and np.array_equal(out[k], serial[k]), "thread %d got another utterance's result" % k
+        # (not bit-identical: a one-shot call may run its second phase for a larger predicted length bucket, whose launches
+        #  split their k-loops differently -- same arithmetic, another summation order; other utterances differ by ~0.1)
+        assert out[k].shape == serial[k].shape and np.abs(out[k] - serial[k]).max() < 2e-5, "thread %d got another utterance's result" % k
 
 
 def test_speculative_second_phase_hits_and_misses(engine, cfg):
@@ -234,7 +238,7 @@ def test_speculative_second_phase_hits_and_misses(engine, cfg):
         ref = engine.synthesize(yl, eps_z)
         wav, yl2 = engine.infer(tok, [T], [1], scales, eps_dp, eps_z, frames_hint=Ty + 40)
         assert int(yl2[0]) == Ty
-        assert np.array_equal(wav[:, : Ty * 256], ref[:, : Ty * 256])
+        assert np.abs(wav[:, : Ty * 256] - ref[:, : Ty * 256]).max() < 2e-5      # (another bucket => another summation order)
     h1, m1 = engine.speculation_stats()
     assert h1 - h0 >= 4 and m1 - m0 >= 1, (h1 - h0, m1 - m0)
 

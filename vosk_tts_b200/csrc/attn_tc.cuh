@@ -96,6 +96,12 @@ __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&r)[8
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t saddr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -172,6 +178,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
         tma_load_2d(sRV + (NC + c) * R_TILE, &ap.rv_lo, c * 64, 0, q_full);
       }
       PDL_WAIT();
+      timeline_stamp_t(-31);
       const int qch = head * DK;
       for (int c = 0; c < NC; ++c) {
         tma_load_2d(sQ + c * Q_TILE, &ap.q_hi, qch + c * 64, (int)base + q0, q_full);
@@ -226,6 +233,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
         umma_commit(&s_full[t & 1]);
       };
       mbar_wait(q_full, 0);
+      timeline_stamp_t(-32);
       tc_fence_after();
       {   // Sr = Q Ek^T (N = 16)
         const uint32_t d = tmem_base + ATC_COL_SR;
@@ -291,8 +299,8 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
     const float scale = 1.0f / sqrtf((float)DK);
     const float L2E = 1.4426950408889634f;
-    float* mySr = sSr + row * ATC_RS;
-    float* myPb = sPb + row * ATC_RS;
+    const uint32_t mySr = smem_u32(sSr + row * ATC_RS);     // (explicit shared-space accesses: generic LD/ST otherwise)
+    const uint32_t myPb = smem_u32(sPb + row * ATC_RS);
     PDL_WAIT();
     {   // relative-key logits of this row -> shared memory (indexed by a run-time offset below)
       mbar_wait(sr_full, 0);
@@ -301,23 +309,25 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
       tmem_ld_x16(tmem_base + lane_sel + ATC_COL_SR, r);
       tmem_wait_ld();
 #pragma unroll
-      for (int m = 0; m < ATC_RS; ++m) mySr[m] = __uint_as_float(r[m]) * scale;
+      for (int m = 0; m < ATC_RS; ++m) sts_f32(mySr + 4 * m, __uint_as_float(r[m]) * scale);
     }
     float m_run = -INFINITY, l_run = 0.f;
     for (int t = 0; t < nt; ++t) {
       const int bsel = t & 1;
       const int k0 = t * ATC_KT;
       mbar_wait(&s_full[bsel], (t >> 1) & 1);
+      if (threadIdx.x == 64) timeline_stamp_t(-40 - t);
       tc_fence_after();
       float s[ATC_KT];
       {
-        uint32_t r[16];
+        uint32_t r0[16], r1[16], r2[16], r3[16];           // all four loads in flight, one wait
+        const uint32_t sa = tmem_base + lane_sel + ATC_COL_S + bsel * ATC_KT;
+        tmem_ld_x16(sa, r0); tmem_ld_x16(sa + 16, r1); tmem_ld_x16(sa + 32, r2); tmem_ld_x16(sa + 48, r3);
+        tmem_wait_ld();
 #pragma unroll
-        for (int n0 = 0; n0 < ATC_KT; n0 += 16) {
-          tmem_ld_x16(tmem_base + lane_sel + ATC_COL_S + bsel * ATC_KT + n0, r);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) s[n0 + i] = __uint_as_float(r[i]) * scale;
+        for (int i = 0; i < 16; ++i) {
+          s[i] = __uint_as_float(r0[i]) * scale; s[16 + i] = __uint_as_float(r1[i]) * scale;
+          s[32 + i] = __uint_as_float(r2[i]) * scale; s[48 + i] = __uint_as_float(r3[i]) * scale;
         }
       }
       // does the +-W band of any row of this CTA / of this warp cross the key tile?
@@ -329,7 +339,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
 #pragma unroll
         for (int c = 0; c < ATC_KT; ++c) {
           const int m = c + moff;
-          if ((unsigned)m < (unsigned)nrel) s[c] += mySr[m];
+          if ((unsigned)m < (unsigned)nrel) s[c] += lds_f32(mySr + 4 * m);
         }
       }
       const int kvalid = len - k0;                   // columns >= kvalid are beyond the utterance
@@ -372,7 +382,7 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
       float lsum = 0.f;
       if (band_cta) {
 #pragma unroll
-        for (int m = 0; m < ATC_RS; ++m) myPb[m] = 0.f;
+        for (int m = 0; m < ATC_RS; ++m) sts_f32(myPb + 4 * m, 0.f);
       }
       {
         uint32_t ph[ATC_KT / 2], pl[ATC_KT / 2];
@@ -382,14 +392,10 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
           lsum += p0 + p1;
           if (band_warp) {
             const int m0 = c + moff, m1 = c + 1 + moff;
-            if ((unsigned)m0 < (unsigned)nrel) myPb[m0] = p0;
-            if ((unsigned)m1 < (unsigned)nrel) myPb[m1] = p1;
+            if ((unsigned)m0 < (unsigned)nrel) sts_f32(myPb + 4 * m0, p0);
+            if ((unsigned)m1 < (unsigned)nrel) sts_f32(myPb + 4 * m1, p1);
           }
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(p0, h0, l0);
-          split_bf16(p1, h1, l1);
-          ph[c >> 1] = pack_bf16(h0, h1);
-          pl[c >> 1] = pack_bf16(l0, l1);
+          split_bf16_pair(p0, p1, ph[c >> 1], pl[c >> 1]);
         }
         l_run += lsum;
         const uint32_t pa = tmem_base + lane_sel + ATC_COL_P + bsel * 64;
@@ -408,12 +414,8 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
         uint32_t bh[8], bl[8];
 #pragma unroll
         for (int m = 0; m < 16; m += 2) {
-          const float p0 = m < ATC_RS ? myPb[m] : 0.f, p1 = m + 1 < ATC_RS ? myPb[m + 1] : 0.f;
-          __nv_bfloat16 h0, l0, h1, l1;
-          split_bf16(p0, h0, l0);
-          split_bf16(p1, h1, l1);
-          bh[m >> 1] = pack_bf16(h0, h1);
-          bl[m >> 1] = pack_bf16(l0, l1);
+          const float p0 = m < ATC_RS ? lds_f32(myPb + 4 * m) : 0.f, p1 = m + 1 < ATC_RS ? lds_f32(myPb + 4 * (m + 1)) : 0.f;
+          split_bf16_pair(p0, p1, bh[m >> 1], bl[m >> 1]);
         }
         const uint32_t pb = tmem_base + lane_sel + ATC_COL_PB + bsel * 16;
         tmem_st_x8(pb, bh);
@@ -423,24 +425,31 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(&p_full[bsel]);
+      if (threadIdx.x == 64) timeline_stamp_t(-60 - t);
     }
     // ---- epilogue: O / l -> fp32 rows and/or split-bf16 planes
     mbar_wait(pv_done, (nt - 1) & 1);
+    if (threadIdx.x == 64) timeline_stamp_t(-36);
     tc_fence_after();
     const float inv = 1.f / l_run;
     const bool rowok = qi < len;
     const long orow = base + qi;
 #pragma unroll
-    for (int n0 = 0; n0 < DK; n0 += 16) {
-      uint32_t r[16];
-      tmem_ld_x16(tmem_base + lane_sel + ATC_COL_O + n0, r);
+    for (int n0 = 0; n0 < DK; n0 += 32) {
+      uint32_t ra[16], rb[16];
+      tmem_ld_x16(tmem_base + lane_sel + ATC_COL_O + n0, ra);
+      tmem_ld_x16(tmem_base + lane_sel + ATC_COL_O + n0 + 16, rb);
       tmem_wait_ld();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+      const uint32_t (&r)[16] = hh ? rb : ra;
+      const int nb = n0 + 16 * hh;
       if (rowok) {
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * inv;
         if (ap.out) {
-          float* o = ap.out + orow * (long)ap.ldo + head * DK + n0;
+          float* o = ap.out + orow * (long)ap.ldo + head * DK + nb;
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
@@ -448,18 +457,20 @@ attn_tc_kernel(const __grid_constant__ AttnTcParams ap, const int* __restrict__ 
           __align__(16) __nv_bfloat16 hb[16], lb[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) split_bf16(v[i], hb[i], lb[i]);
-          __nv_bfloat16* ph = ap.p_hi + orow * (long)ap.ldp + head * DK + n0;
-          __nv_bfloat16* pl = ap.p_lo + orow * (long)ap.ldp + head * DK + n0;
+          __nv_bfloat16* ph = ap.p_hi + orow * (long)ap.ldp + head * DK + nb;
+          __nv_bfloat16* pl = ap.p_lo + orow * (long)ap.ldp + head * DK + nb;
           *reinterpret_cast<uint4*>(ph) = *reinterpret_cast<const uint4*>(hb);
           *reinterpret_cast<uint4*>(ph + 8) = *reinterpret_cast<const uint4*>(hb + 8);
           *reinterpret_cast<uint4*>(pl) = *reinterpret_cast<const uint4*>(lb);
           *reinterpret_cast<uint4*>(pl + 8) = *reinterpret_cast<const uint4*>(lb + 8);
         }
       }
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) timeline_stamp_t(-37);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)ATC_TMEM_COLS) : "memory");

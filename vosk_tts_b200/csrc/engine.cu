@@ -60,7 +60,7 @@ struct TcSpec {  // one problem of a grouped tensor-core conv launch
   const float* res = nullptr; int ldr = 0;
   Planes out; float pl_slope = 1.f;
   int out_mul = 1, out_add = 0, in_extra = 0, out_seq_extra = 0;
-  int yoff = 0, roff = 0, epi = 0;
+  int yoff = 0, roff = 0, epi = 0, poff = 0;
   float alpha = 1.f;
   const float* cond = nullptr; int cond_ld = 0;
 };
@@ -200,7 +200,7 @@ struct vtts_engine {
   float spec_ratio = 0.f;
   uint64_t spec_hits = 0, spec_misses = 0;
   double spec_units() const { return (double)real_maxTok * (double)std::max(0.05f, scales[1]); }
-  int spec_predict() const { return (int)std::ceil((double)spec_ratio * 1.04 * spec_units()) + 4; }
+  int spec_predict() const { return (int)std::ceil((double)spec_ratio * 1.08 * spec_units()) + 8; }
   void spec_learn() {
     spec_hist[spec_n++ % 16] = (float)((double)real_maxFrm / spec_units());
     float m = 0.f;
@@ -264,7 +264,7 @@ struct vtts_engine {
   std::vector<int> h_tok_len, h_tok_off, h_frm_len, h_frm_off;
 
   // ---- workspace
-  Buf<int> d_ids, d_tok_len, d_tok_off, d_sid, d_wceil, d_cum, d_frm_len, d_frm_off, d_ftok;
+  Buf<int> d_ids, d_tok_len, d_tok_off, d_sid, d_wceil, d_cum, d_frm_len, d_frm_off, d_ftok, d_done_ctr;
   Buf<float> d_condv, d_x, d_xb, d_qkv, d_ao, d_y, d_ffh, d_stats, d_dA, d_dB, d_dx, d_h29, d_za, d_zb, d_eps_dp;
   Buf<float> d_z, d_h, d_h1, d_wx, d_acts, d_skip, d_fqkv, d_fao, d_fy, d_ffh2, d_eps_z, d_d0, d_post, d_wav;
   std::vector<Buf<float>> d_stage;               // X_i
@@ -288,13 +288,14 @@ struct vtts_engine {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; uint64_t gen = 0; uint64_t used = 0; uint64_t nlaunch = 0; int seen = 0; };
   std::map<std::vector<long long>, GraphEntry> graphs;
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
+  bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
   int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
-  bool attn_tc = true;                     // tcgen05 attention wherever the qkv conv runs on tensor cores (VTTS_ATTN_TC=0: FFMA attention)
+  int attn_tc_mode = 1;                    // tcgen05 attention where the qkv conv runs on tensor cores: 0 never, 1 when throughput bound, 2 always
   int mrf_branch = 0;                      // VTTS_MRF_BRANCH=1: one stream per resblock chain (measured slower: 1.74 vs 1.62 ms)
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -329,8 +330,9 @@ struct vtts_engine {
   }
   char* ensure_pinned(size_t n) { return ensure_pinned(h_pin, n); }
 
-  // Runs `enqueue` (which only enqueues work on `stream`) eagerly the first time a shape key is seen, captures it
-  // into a CUDA graph the second time, and replays the graph afterwards.  The key is the full tuple of everything the
+  // Runs `enqueue` (which only enqueues work on `stream`) eagerly the first time a shape key is seen -- that run also
+  // performs every workspace growth -- and right behind it records the same work into a CUDA graph (capture only, no second
+  // execution), so that the SECOND call of a bucket already replays.  The key is the full tuple of everything the
   // enqueued work depends on besides device-resident data (phase tag, batch, length buckets, noise mode, raw pointers of
   // the *_dev entry points): entries are compared on the tuple itself, so there is no hash collision to replay a wrong
   // graph on.  The cache is bounded (LRU, checked on every insertion).
@@ -360,8 +362,12 @@ struct vtts_engine {
       last_graphed = true;
       return;
     }
-    if (g.seen++ == 0) { enqueue(); return; }   // first sighting: eager (also performs any workspace growth)
-    const uint64_t gen0 = ws_gen, l0 = launches;
+    const bool first = (g.seen++ == 0);
+    if (first) {                                // first sighting: eager (also performs any workspace growth) ...
+      enqueue();
+      if (!capture_on_first) return;
+    }
+    const uint64_t gen0 = ws_gen, l0 = launches;      // ... then capture
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
     capturing = true;
@@ -382,6 +388,7 @@ struct vtts_engine {
     g.exec = exec;
     g.gen = gen0;
     g.nlaunch = launches - l0;
+    if (first) { launches = l0; return; }       // (the eager run above already did the work)
     CK(cudaGraphLaunch(g.exec, stream));
     ++graph_replays;
     last_graphed = true;
@@ -421,26 +428,28 @@ struct vtts_engine {
     }
     return t.p;
   }
-  ConvW conv(const std::string& name, int Cin, int Cout, int k) {
+  // need_w = false: the conv runs on tcgen05 from its split-bf16 copy in this precision mode; the fp32 copy is bound only if
+  // the blob happens to carry it (weights.pack(precision=...) leaves it out of the one-time weight broadcast)
+  ConvW conv(const std::string& name, int Cin, int Cout, int k, bool need_w = true) {
     ConvW c;
     c.Cin = Cin; c.Cout = Cout; c.k = k; c.ldw = (Cout + 3) / 4 * 4;
-    c.w = vec(name + ".w", (size_t)k * Cin * c.ldw);
+    if (need_w || tensors.count(name + ".w")) c.w = vec(name + ".w", (size_t)k * Cin * c.ldw);
     c.b = vec(name + ".b", (size_t)c.ldw);
     REQUIRE(Cin % CV_CK == 0, VTTS_ERR_INVALID, "conv input channels must be a multiple of 16");
     return c;
   }
   LnW ln(const std::string& name, int C) { return LnW{vec(name + ".g", C), vec(name + ".b", C)}; }
-  EncLayerW enc_layer(const std::string& p, int Hc, int Fc, int ks, int heads) {
+  EncLayerW enc_layer(const std::string& p, int Hc, int Fc, int ks, int heads, bool need_w = true) {
     EncLayerW L;
     L.heads = heads;
     const int dk = Hc / heads, nrel = 2 * cfg.window_size + 1;
-    L.qkv = conv(p + ".qkv", Hc, 3 * Hc, 1);
-    L.o = conv(p + ".o", Hc, Hc, 1);
+    L.qkv = conv(p + ".qkv", Hc, 3 * Hc, 1, need_w);
+    L.o = conv(p + ".o", Hc, Hc, 1, need_w);
     L.relk = vec(p + ".relk", (size_t)nrel * dk);
     L.relv = vec(p + ".relv", (size_t)nrel * dk);
     L.ln1 = ln(p + ".ln1", Hc);
-    L.ffn1 = conv(p + ".ffn1", Hc, Fc, ks);
-    L.ffn2 = conv(p + ".ffn2", Fc, Hc, ks);
+    L.ffn1 = conv(p + ".ffn1", Hc, Fc, ks, need_w);
+    L.ffn2 = conv(p + ".ffn2", Fc, Hc, ks, need_w);
     L.ln2 = ln(p + ".ln2", Hc);
     return L;
   }
@@ -491,17 +500,25 @@ struct vtts_engine {
   }
   CUtensorMap make_map(const void* base, int C, long rows, int box_rows);
   bool attn_tc_ok(const EncLayerW& L, int Hc) const;
+  bool attn_use_tc(const EncLayerW& L, int Hc, const int* lens, int maxLen) const;
   void launch_attn_tc(const Planes& qkv, float* ao, Planes* pl, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen);
   void launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
-  void decoder_tc(float* z, const int* fl, const int* fo);
-  void flow_tc(float* z, const int* fl, const int* fo);
+  // plane buffers of the frame-resolution stages: allocated (and their tails zeroed by ONE zero_tails launch) before the
+  // first kernel of the phase
+  struct FlowPl { Planes ph, pao, ph1, pff, pwx, pacts, pskip, pqkv; } flp;
+  struct DecPl { Planes pz, cur; std::vector<Planes> px, nxt; std::vector<std::vector<Planes>> pj, pt; } dcp;
+  void alloc_flow_planes();
+  void alloc_decoder_planes();
+  void decoder_tc(float* z, const int* fl, const int* fo, bool pz_ready);
+  void flow_tc(float* z, const int* fl, const int* fo, bool emit_pz);
   void launch_attn(const float* qkv, float* ao, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen, Planes* pl);
   void bind_weights();
   void launch_conv(const std::vector<ConvP>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   void encoder_layer(const EncLayerW& L, float*& x, float*& xb, float* qkv, float* ao, float* y, float* ffh, int Hc, int Fc,
                      int ks, const int* lens, const int* offs, int maxLen, const float* vec_after, int vec_ld,
                      const float* cadd_after);
-  void dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, const int* lens, const int* offs, int maxLen);
+  void dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, const int* lens, const int* offs, int maxLen,
+                 const float* x0 = nullptr, const float* pre_w = nullptr, const float* pre_b = nullptr, const float* cond = nullptr);
   struct P1Pin { int *len, *off, *sid, *ids; float *prm, *eps; };
   P1Pin p1_layout(int t_max, bool eps);
   void stage1(const int* ids_packed_host, const int* sid_host, int t_max, const float* noise_dp_host);
@@ -515,7 +532,7 @@ struct vtts_engine {
     const size_t ncopy = (size_t)std::min(z_ld, maxFrm);
     for (long r = 0; r < (long)B * I; ++r) memcpy(pin + r * maxFrm, noise_z + r * (long)z_ld, ncopy * sizeof(float));
   }
-  void decode(float* z, const int* fl, const int* fo);
+  void decode(float* z, const int* fl, const int* fo, bool planes_ready = false, bool pz_ready = false);
   bool have_latent = false;
   Buf<int> d_chunk;                              // [len, off, off_end] of the chunk being decoded
 };
@@ -593,9 +610,9 @@ void vtts_engine::bind_weights() {
   }
   enc_emb = vec("enc.emb", (size_t)c.n_vocab * H);
   enc.clear();
-  for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size, c.n_heads));
-  enc_proj = conv("enc.proj", H, 2 * I, 1);
   enc_on_tc = c.precision == 2 && H % TC_BK == 0 && c.filter_channels % TC_BK == 0;
+  for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size, c.n_heads, !enc_on_tc));
+  enc_proj = conv("enc.proj", H, 2 * I, 1, !enc_on_tc);
   if (enc_on_tc) {
     for (int i = 0; i < c.n_layers; ++i) {
       const std::string p = "enc." + std::to_string(i);
@@ -625,14 +642,15 @@ void vtts_engine::bind_weights() {
   for (int f = 0; f < nf; ++f) {
     FlowW F;
     const std::string p = "flow." + std::to_string(f);
+    const bool fw = !(c.precision >= 1 && H % TC_BK == 0);       // fp32 copies needed? (no: the whole flow but its pre conv is on tcgen05)
     F.pre = conv(p + ".pre", I / 2, H, 1);
-    if (c.use_transformer_flows) F.tr = enc_layer(p + ".tr", H, H, c.flow_kernel_size, fheads);
+    if (c.use_transformer_flows) F.tr = enc_layer(p + ".tr", H, H, c.flow_kernel_size, fheads, fw);
     for (int i = 0; i < nl; ++i) {
-      F.in.push_back(conv(p + ".in" + std::to_string(i), H, 2 * H, c.flow_kernel_size));
-      if (i < nl - 1) F.rsx.push_back(conv(p + ".rsx" + std::to_string(i), H, H, 1));
-      F.rss.push_back(conv(p + ".rss" + std::to_string(i), H, H, 1));
+      F.in.push_back(conv(p + ".in" + std::to_string(i), H, 2 * H, c.flow_kernel_size, fw));
+      if (i < nl - 1) F.rsx.push_back(conv(p + ".rsx" + std::to_string(i), H, H, 1, fw));
+      F.rss.push_back(conv(p + ".rss" + std::to_string(i), H, H, 1, fw));
     }
-    F.post = conv(p + ".post", H, I / 2, 1);
+    F.post = conv(p + ".post", H, I / 2, 1, fw);
     if (c.precision >= 1 && H % TC_BK == 0) {
       const int fk = c.flow_kernel_size;
       if (c.use_transformer_flows) {
@@ -651,8 +669,8 @@ void vtts_engine::bind_weights() {
     }
     flow.push_back(F);
   }
-  dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7);
   tc = c.precision == 1 || c.precision == 2;
+  dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7, !tc);
   if (tc) {
     REQUIRE(c.decoder_type == 0 && c.resblock_type == 1, VTTS_ERR_INVALID, "tensor-core mode supports the MB-iSTFT / ResBlock1 decoder");
     tc_pre = tcw("dec.pre", I, c.upsample_initial_channel, 7);
@@ -668,7 +686,7 @@ void vtts_engine::bind_weights() {
       // polyphase split of ConvTranspose1d (see weights.convt_phases): taps per phase and left padding
       int d_min = -((r + p) / u);
       int d_max = (K - 1 - r - p) / u;
-      U.phase.push_back(conv("dec.up" + std::to_string(i) + ".p" + std::to_string(r), ch, ch / 2, d_max - d_min + 1));
+      U.phase.push_back(conv("dec.up" + std::to_string(i) + ".p" + std::to_string(r), ch, ch / 2, d_max - d_min + 1, !tc));
       if (tc) U.tphase.push_back(tcw("dec.up" + std::to_string(i) + ".p" + std::to_string(r), ch, ch / 2, d_max - d_min + 1));
       U.pad.push_back(d_max);
     }
@@ -680,8 +698,8 @@ void vtts_engine::bind_weights() {
       const std::string p2 = "dec.rb" + std::to_string(i * c.n_resblock_kernels + j);
       for (int d = 0; d < c.n_resblock_dilations; ++d) {
         if (c.resblock_type == 1) {
-          R.c1.push_back(conv(p2 + ".c1." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
-          R.c2.push_back(conv(p2 + ".c2." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
+          R.c1.push_back(conv(p2 + ".c1." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j], !tc));
+          R.c2.push_back(conv(p2 + ".c2." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j], !tc));
           if (tc) {
             R.t1.push_back(tcw(p2 + ".c1." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
             R.t2.push_back(tcw(p2 + ".c2." + std::to_string(d), ch, ch, c.resblock_kernel_sizes[j]));
@@ -697,7 +715,7 @@ void vtts_engine::bind_weights() {
   }
   if (c.decoder_type == 0) {
     const int cps = c.istft_n_fft + 2;
-    dec_post = conv("dec.post", ch, c.subbands * cps, 7);
+    dec_post = conv("dec.post", ch, c.subbands * cps, 7, !tc);
     if (tc) tc_post = tcw("dec.post", ch, c.subbands * cps, 7);
     istft_basis = vec("dec.istft", (size_t)cps * c.istft_n_fft);
     pqmf = vec("dec.pqmf", (size_t)c.subbands * 63);
@@ -811,7 +829,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     P.res = q.res; P.ldr = q.ldr; P.roff = q.roff;
     P.y = q.y; P.ldy = q.ldy; P.yoff = q.yoff;
     P.cond = q.cond; P.cond_ld = q.cond_ld; P.epi = q.epi;
-    P.p_hi = q.out.hi; P.p_lo = q.out.lo; P.ldp = q.out.C;
+    P.p_hi = q.out.hi; P.p_lo = q.out.lo; P.ldp = q.out.C; P.poff = q.poff;
     P.Cin = q.Cin; P.Cout = q.Cout; P.k = q.k; P.dil = q.dil; P.pad = q.pad;
     P.out_mul = q.out_mul; P.out_add = q.out_add; P.in_extra = q.in_extra; P.out_seq_extra = q.out_seq_extra;
     P.alpha = q.alpha; P.pl_slope = q.pl_slope;
@@ -876,8 +894,24 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
 // Attention on the tensor cores (attn_tc.cuh): q, k, v come as the split-bf16 planes the qkv conv's epilogue wrote.
 bool vtts_engine::attn_tc_ok(const EncLayerW& L, int Hc) const {
   const int dk = Hc / L.heads;
-  return attn_tc && L.rk_hi != nullptr && dk % 32 == 0 && dk <= 128 && 2 * cfg.window_size + 1 <= ATC_RS && (3 * Hc) % 8 == 0;
+  return attn_tc_mode > 0 && L.rk_hi != nullptr && dk % 32 == 0 && dk <= 128 && 2 * cfg.window_size + 1 <= ATC_RS && (3 * Hc) % 8 == 0;
 }
+// Which attention kernel for this launch?  The tensor-core kernel wins as soon as the launch is throughput bound (batches,
+// long utterances: 8.8x at 4765 frames, 2.8x on the flow of a 64-utterance batch).  A single short utterance is latency
+// bound -- a 128-row tcgen05 tile walks its 2-4 key tiles serially while the split-KV FFMA kernel spreads 4 query rows x 4
+// key segments over 16 warps of ~80 CTAs -- and keeps the FFMA kernel (measured at 162 frames: 6 vs 19 us per launch in the
+// graph).  VTTS_ATTN_TC = 0 never / 1 this rule / 2 always.
+bool vtts_engine::attn_use_tc(const EncLayerW& L, int Hc, const int* lens, int maxLen) const {
+  if (!attn_tc_ok(L, Hc)) return false;
+  if (attn_tc_mode >= 2) return true;
+  const std::vector<int>& hl = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
+  long ctas = 0;
+  for (int b = 0; b < B; ++b) ctas += (long)((hl[b] + ATS_ROWS - 1) / ATS_ROWS) * L.heads;
+  const int mt = (maxLen + AT_KT - 1) / AT_KT;
+  const bool split_kv_fits = attn_split && (attn_rows == 0 || attn_rows == 1) && mt <= ATS_MAXT && ctas <= 148;
+  return !split_kv_fits;
+}
+
 void vtts_engine::launch_attn_tc(const Planes& qkv, float* ao, Planes* pl, const EncLayerW& L, int Hc, const int* lens, const int* offs, int maxLen) {
   const int dk = Hc / L.heads;
   AttnTcParams ap;
@@ -950,7 +984,37 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
 // Flow (reverse, models.py:750-757) with every dense conv on the tensor cores.  Producers emit the split-bf16
 // planes their consumer needs: FFMA pre-conv, attention and LayerNorm kernels through an extra epilogue output,
 // tensor-core convs through theirs.  The Flip folding is the same as in the fp32 path.
-void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
+void vtts_engine::alloc_flow_planes() {
+  const int H = cfg.hidden_channels;
+  const long F = Tfrm;
+  int slot = 40;    // plane slots 40.. are the flow's (the decoder uses 0..)
+  flp.ph = planes(slot++, F, 1, H); flp.pao = planes(slot++, F, 1, H); flp.ph1 = planes(slot++, F, 1, H);
+  flp.pff = planes(slot++, F, 1, H); flp.pwx = planes(slot++, F, 1, H); flp.pacts = planes(slot++, F, 1, H);
+  flp.pskip = planes(slot++, F, 1, H);
+  flp.pqkv = planes(slot++, F, 1, 3 * H);
+}
+void vtts_engine::alloc_decoder_planes() {
+  const vtts_config& c = cfg;
+  const long F = Tfrm;
+  const int nk = c.n_resblock_kernels;
+  int slot = 0;
+  dcp.pz = planes(slot++, F, 1, c.inter_channels);
+  dcp.cur = planes(slot++, F, 1, c.upsample_initial_channel);
+  dcp.px.resize(c.n_upsamples); dcp.nxt.resize(c.n_upsamples); dcp.pj.resize(c.n_upsamples); dcp.pt.resize(c.n_upsamples);
+  int rmp = 1, chp = c.upsample_initial_channel;
+  for (int i = 0; i < c.n_upsamples; ++i) {
+    rmp *= c.upsample_rates[i];
+    chp /= 2;
+    dcp.px[i] = planes(slot++, F, rmp, chp);
+    dcp.pj[i].resize(nk); dcp.pt[i].resize(nk);
+    for (int j = 0; j < nk; ++j) { dcp.pj[i][j] = planes(slot++, F, rmp, chp); dcp.pt[i][j] = planes(slot++, F, rmp, chp); }
+    dcp.nxt[i] = planes(slot++, F, rmp, chp, (i + 1 == c.n_upsamples) ? 1 : 0);
+  }
+}
+
+// emit_pz: the post convs of the last two coupling layers also write the split-bf16 planes of their half of z for the
+// decoder's conv_pre (dcp.pz), which saves the separate fp32 -> planes pass
+void vtts_engine::flow_tc(float* z, const int* fl, const int* fo, bool emit_pz) {
   const vtts_config& c = cfg;
   const int H = c.hidden_channels, I = c.inter_channels, half = I / 2;
   const long F = Tfrm;
@@ -962,13 +1026,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
   float* fy = ensure(d_fy, (size_t)F * H);
   float* fqkv = ensure(d_fqkv, (size_t)F * 3 * H);
   float* fao = ensure(d_fao, (size_t)F * H);
-  int slot = 40;    // plane slots 40.. are the flow's (the decoder uses 0..)
-  begin_planes();
-  Planes ph = planes(slot++, F, 1, H), pao = planes(slot++, F, 1, H), ph1 = planes(slot++, F, 1, H);
-  Planes pff = planes(slot++, F, 1, H), pwx = planes(slot++, F, 1, H), pacts = planes(slot++, F, 1, H);
-  Planes pskip = planes(slot++, F, 1, H);
-  Planes pqkv = planes(slot++, F, 1, 3 * H);
-  flush_tails(fl, fo);
+  Planes ph = flp.ph, pao = flp.pao, ph1 = flp.ph1, pff = flp.pff, pwx = flp.pwx, pacts = flp.pacts, pskip = flp.pskip, pqkv = flp.pqkv;
   dim3 lg((maxFrm + 3) / 4, B);
   for (int f = nf - 1; f >= 0; --f) {
     const FlowW& W = flow[f];
@@ -982,7 +1040,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
     }
     float* wn_x = h;
     if (c.use_transformer_flows) {
-      if (attn_tc_ok(W.tr, H)) {
+      if (attn_use_tc(W.tr, H, fl, maxFrm)) {
         // q, k, v leave the qkv conv as split-bf16 planes only; attention runs on tcgen05 (attn_tc.cuh)
         { TcSpec q; q.in = ph; q.w = W.t_qkv; q.bias = W.tr.qkv.b; q.Cin = H; q.Cout = 3 * H; q.out = pqkv; q.pl_slope = 1.f;
           launch_tc({q}, 1, fl, fo, maxFrm, B); }
@@ -1028,37 +1086,22 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo) {
     }
     { TcSpec q; q.in = pskip; q.w = W.t_post; q.bias = W.post.b; q.Cin = H; q.Cout = half; q.alpha = -1.f;
       q.y = z; q.ldy = I; q.yoff = x1off; q.res = z; q.ldr = I; q.roff = x1off;
+      if (emit_pz && f <= 1) { q.out = dcp.pz; q.poff = x1off; q.pl_slope = 1.f; }     // this half of z is final now
       launch_tc({q}, 1, fl, fo, maxFrm, B); }
   }
 }
 
 // Decoder on the tensor cores (models.py:1016-1040): every conv consumes the split-bf16 planes written by its
 // producer's epilogue; fp32 copies exist only where a residual or the MRF mean needs them.
-void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo) {
+void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo, bool pz_ready) {
   const vtts_config& c = cfg;
   const int I = c.inter_channels;
   const long F = Tfrm;
   const int nk = c.n_resblock_kernels, nd = c.n_resblock_dilations;
-  int slot = 0;
-  // every plane buffer of the decoder, allocated (and its tails zeroed) before the first launch
-  begin_planes();
-  Planes pz = planes(slot++, F, 1, I);
-  Planes cur = planes(slot++, F, 1, c.upsample_initial_channel);
-  std::vector<Planes> st_px(c.n_upsamples), st_nxt(c.n_upsamples);
-  std::vector<std::vector<Planes>> st_pj(c.n_upsamples), st_pt(c.n_upsamples);
-  {
-    int rmp = 1, chp = c.upsample_initial_channel;
-    for (int i = 0; i < c.n_upsamples; ++i) {
-      rmp *= c.upsample_rates[i];
-      chp /= 2;
-      st_px[i] = planes(slot++, F, rmp, chp);
-      st_pj[i].resize(nk); st_pt[i].resize(nk);
-      for (int j = 0; j < nk; ++j) { st_pj[i][j] = planes(slot++, F, rmp, chp); st_pt[i][j] = planes(slot++, F, rmp, chp); }
-      st_nxt[i] = planes(slot++, F, rmp, chp, (i + 1 == c.n_upsamples) ? 1 : 0);
-    }
-  }
-  flush_tails(fl, fo);
-  {
+  Planes pz = dcp.pz, cur = dcp.cur;
+  const std::vector<Planes>&st_px = dcp.px, &st_nxt = dcp.nxt;
+  const std::vector<std::vector<Planes>>&st_pj = dcp.pj, &st_pt = dcp.pt;
+  if (!pz_ready) {
     dim3 g(maxFrm, B);
     klaunch(split_planes_kernel, dim3(g), dim3(64), (size_t)(0), z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
     CK(cudaGetLastError());
@@ -1305,11 +1348,13 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
   ++launches;
 }
 
-void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, const int* lens, const int* offs, int maxLen) {
+void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, const int* lens, const int* offs, int maxLen,
+                            const float* x0, const float* pre_w, const float* pre_b, const float* cond) {
   int dil = 1;
   for (int i = 0; i < 3; ++i) {
     DdsP P;
     P.x = a; P.y = b;
+    P.x0 = (i == 0) ? x0 : nullptr; P.pre_w = pre_w; P.pre_b = pre_b; P.cond = cond;
     P.sep_w = d[i].sep_w; P.sep_b = d[i].sep_b;
     P.ln1g = d[i].ln1.g; P.ln1b = d[i].ln1.b;
     P.pw_w = d[i].pw.w; P.pw_b = d[i].pw.b; P.ldw = d[i].pw.ldw;
@@ -1414,7 +1459,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     const EncLayerW& L = enc[i];
     const int ks = c.kernel_size;
     dim3 lg((maxTok + 3) / 4, B);
-    if (attn_tc_ok(L, H)) {
+    if (attn_use_tc(L, H, tl, maxTok)) {
       { TcSpec q; q.in = px; q.w = L.t_qkv; q.bias = L.qkv.b; q.Cin = H; q.Cout = 3 * H; q.out = pqkv; q.pl_slope = 1.f;
         launch_tc({q}, 1, tl, to, maxTok, B); }
       launch_attn_tc(pqkv, nullptr, &pao, L, H, tl, to, maxTok);
@@ -1469,14 +1514,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   REQUIRE(3 * nbins - 1 <= 32, VTTS_ERR_INVALID, "spline parameter row too wide");
   for (int n = c.dp_n_flows; n >= 2; --n) {
     const CfW& F = cf[n - 2];
-    {
-      dim3 g(maxTok, B);
-      klaunch(cf_pre_kernel, dim3(g), dim3(128), (size_t)(0), cvar, F.pre_w, F.pre_b, dx, dA, tl, to, D);
-      CK(cudaGetLastError());
-      ++launches;
-    }
+    // (the ConvFlow front h = pre(x0) + cond, modules.py:366-367, is computed inside the first DDS layer)
     float *a = dA, *b = dB;
-    dds_stack(F.dds, D, c.dp_kernel_size, a, b, tl, to, maxTok);
+    dds_stack(F.dds, D, c.dp_kernel_size, a, b, tl, to, maxTok, cvar, F.pre_w, F.pre_b, dx);
     launch_conv({mk(F.proj, a, D, 0, h29, 32, 0, 1, 0)}, 1, tl, to, maxTok, B);
     {
       dim3 g((maxTok + 127) / 128, B);
@@ -1492,11 +1532,11 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   int* cum = ensure(d_cum, T);
   int* fl = ensure(d_frm_len, B);
   int* fo = ensure(d_frm_off, B + 1);
-  klaunch(duration_kernel, dim3(B), dim3(256), (size_t)(0), zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to);
+  unsigned int* dctr = reinterpret_cast<unsigned int*>(ensure(d_done_ctr, 4));
+  klaunch(duration_kernel, dim3(B), dim3(256), (size_t)(0), zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to, fo, B,
+          (volatile int*)(use_poll ? d_map : nullptr), dctr);
   CK(cudaGetLastError());
-  klaunch(frame_offsets_kernel, dim3(1), dim3(32), (size_t)(0), fl, fo, B, (volatile int*)(use_poll ? d_map : nullptr), (const float*)prm);
-  CK(cudaGetLastError());
-  launches += 2;
+  ++launches;
   if (!capturing) CK(cudaEventRecord(ev[3], stream));
   if (!use_poll) {
     int* p_len = reinterpret_cast<int*>(ensure_pinned(h_pin_len, (size_t)(2 * B + 2) * sizeof(int)));
@@ -1640,7 +1680,15 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
   }
   const int nf = c.flow_n_flows, nl = c.flow_wn_layers, fk = c.flow_kernel_size;
   const bool flow_on_tc = tc && !flow.empty() && !flow[0].t_in.empty();
-  if (flow_on_tc) flow_tc(z, fl, fo);
+  const bool dec_now = tc && run_decoder;
+  const bool emit_pz = flow_on_tc && dec_now && nf >= 2 && !(debug_flags & 2);
+  if (flow_on_tc || dec_now) {
+    begin_planes();
+    if (flow_on_tc) alloc_flow_planes();
+    if (dec_now) alloc_decoder_planes();
+    flush_tails(fl, fo);
+  }
+  if (flow_on_tc) flow_tc(z, fl, fo, emit_pz);
   for (int f = nf - 1; f >= 0 && !flow_on_tc; --f) {
     const FlowW& W = flow[f];
     const bool flipped = ((nf - f) % 2) == 1;
@@ -1701,18 +1749,23 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
   if (!capturing) CK(cudaEventRecord(ev[5], stream));
 
   if (!run_decoder) return;
-  decode(z, fl, fo);
+  decode(z, fl, fo, /*planes_ready=*/dec_now, /*pz_ready=*/emit_pz);
 }
 
 // Decoder over the utterance rows described by (fl, fo) -- the whole batch, or one halo-extended chunk of a single
 // utterance (vtts_decode_chunk).
-void vtts_engine::decode(float* z, const int* fl, const int* fo) {
+void vtts_engine::decode(float* z, const int* fl, const int* fo, bool planes_ready, bool pz_ready) {
   const vtts_config& c = cfg;
   const int I = c.inter_channels;
   const size_t F = (size_t)Tfrm;
   // ---- decoder (models.py:1016-1054 / 872-891)
   if (tc) {
-    decoder_tc(z, fl, fo);
+    if (!planes_ready) {          // (chunked decoding: the decoder runs on its own)
+      begin_planes();
+      alloc_decoder_planes();
+      flush_tails(fl, fo);
+    }
+    decoder_tc(z, fl, fo, pz_ready);
     if (!capturing) CK(cudaEventRecord(ev[6], stream));
     return;
   }
@@ -1941,7 +1994,7 @@ static void impl_synthesize(vtts_handle h, const float* noise_z, int z_ld, float
   REQUIRE(!frame_token || idx_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "frame_token has fewer columns than max(y_lengths)");
   if (noise_z) h->stage_noise_z(noise_z, z_ld);
   // graph key = the length BUCKETS (token rows, frame rows), not the lengths: kernels read the true lengths on the device
-  h->run_graphed({0x22, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
+  h->run_graphed({0x22, h->B, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
   const size_t nw = (size_t)h->real_Tfrm * h->hop;
   char* pin = h->ensure_pinned((size_t)h->Tfrm * h->hop * sizeof(float) + (size_t)h->Tfrm * sizeof(int) + 64);
   float* pw = reinterpret_cast<float*>(pin);
@@ -1992,7 +2045,7 @@ static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths
     h->assume_frames(h->spec_predict());
     const int cap = h->maxFrm;
     if (noise_z) h->stage_noise_z(noise_z, z_ld);
-    h->run_graphed({0x22, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
+    h->run_graphed({0x22, h->B, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
     // the true length is not known on the host yet: the bucket's worth of samples comes back
     const size_t ncap = (size_t)cap * h->hop;
     char* pin = h->ensure_pinned(ncap * sizeof(float) + (size_t)cap * sizeof(int) + 64);
@@ -2039,7 +2092,7 @@ static void impl_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* l
   if (spec_ok(h, B)) {
     h->assume_frames(h->spec_predict());
     const int cap = h->maxFrm;
-    h->run_graphed({0x44, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
+    h->run_graphed({0x44, h->B, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
     const size_t ncopy = (size_t)std::min<int64_t>((int64_t)cap * h->hop, wav_ld);
     CK(cudaMemcpyAsync(d_wav, h->d_wav.p, ncopy * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
@@ -2074,7 +2127,7 @@ static void impl_synthesize_dev(vtts_handle h, const float* d_noise_z, int z_ld,
   REQUIRE(h->have_durations, VTTS_ERR_STATE, "vtts_synthesize_dev called without vtts_durations_dev");
   REQUIRE((int64_t)h->real_maxFrm * h->hop <= wav_ld, VTTS_ERR_CAPACITY, "wav_ld is smaller than hop * max(y_lengths)");
   REQUIRE(!d_noise_z || z_ld >= h->real_maxFrm, VTTS_ERR_CAPACITY, "noise_z has fewer columns than max(y_lengths)");
-  h->run_graphed({0x44, h->B, h->maxTok, h->Ttok, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
+  h->run_graphed({0x44, h->B, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
   for (int b = 0; b < h->B; ++b)
     CK(cudaMemcpyAsync(d_wav + (size_t)b * wav_ld, h->d_wav.p + (size_t)h->h_frm_off[b] * h->hop,
                        (size_t)h->h_frm_len[b] * h->hop * sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
@@ -2157,15 +2210,17 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
     if (const char* e = getenv("VTTS_ATTN_ROWS")) h->attn_rows = atoi(e);
-    if (const char* e = getenv("VTTS_ATTN_TC")) h->attn_tc = atoi(e) != 0;
+    if (const char* e = getenv("VTTS_ATTN_TC")) h->attn_tc_mode = atoi(e);
     if (const char* e = getenv("VTTS_PDL")) h->use_pdl = atoi(e) != 0;
     if (const char* e = getenv("VTTS_NO_POLL")) h->use_poll = atoi(e) == 0;
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("VTTS_BUCKETS")) h->use_buckets = atoi(e) != 0;
-    if (const char* e = getenv("VTTS_SPEC")) h->use_spec = atoi(e) != 0;          // 0: never enqueue phase 2 before the lengths are known    // 0: size everything by the exact lengths
+    if (const char* e = getenv("VTTS_SPEC")) h->use_spec = atoi(e) != 0;
+    if (const char* e = getenv("VTTS_CAPTURE_FIRST")) h->capture_on_first = atoi(e) != 0;   // 0: capture a bucket's graph on its second call          // 0: never enqueue phase 2 before the lengths are known    // 0: size everything by the exact lengths
     if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
     h->build_prefetch_list();
+    CK(cudaMemsetAsync(h->ensure(h->d_done_ctr, 4), 0, 4 * sizeof(int), h->stream));     // ticket counter of duration_kernel (self-resetting)
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(32)));
     CK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(64)));
@@ -2196,7 +2251,7 @@ void vtts_destroy(vtts_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->d_blob);
-  Buf<int>* ib[] = {&h->d_ids, &h->d_tok_len, &h->d_tok_off, &h->d_sid, &h->d_wceil, &h->d_cum, &h->d_frm_len, &h->d_frm_off, &h->d_ftok};
+  Buf<int>* ib[] = {&h->d_ids, &h->d_tok_len, &h->d_tok_off, &h->d_sid, &h->d_wceil, &h->d_cum, &h->d_frm_len, &h->d_frm_off, &h->d_ftok, &h->d_done_ctr};
   for (auto* b : ib) fr(b->p);
   Buf<float>* fb[] = {&h->d_condv, &h->d_x, &h->d_xb, &h->d_qkv, &h->d_ao, &h->d_y, &h->d_ffh, &h->d_stats, &h->d_dA, &h->d_dB, &h->d_dx,
                       &h->d_h29, &h->d_za, &h->d_zb, &h->d_eps_dp, &h->d_z, &h->d_h, &h->d_h1, &h->d_wx, &h->d_acts, &h->d_skip, &h->d_fqkv,

@@ -34,6 +34,16 @@ __device__ __forceinline__ void timeline_stamp(int line) {
 // so on -- inside a CUDA graph the whole chain piles onto the SMs spinning in griddepcontrol.wait (measured: slower).
 // Triggering after the wait keeps exactly one successor in flight: its launch latency and prologue overlap this
 // kernel's main work.
+// same, for one designated thread of CTA (0,0,0) that is not thread 0 (warp-specialised kernels)
+__device__ __forceinline__ void timeline_stamp_t(int line) {
+  unsigned long long* tl = g_timeline;
+  if (tl && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const unsigned long long i = atomicAdd(tl, 1ull);
+    if (i < 4000) { tl[1 + 2 * i] = (unsigned long long)line; tl[2 + 2 * i] = t; }
+  }
+}
 #define PDL_LAUNCH() timeline_stamp(__LINE__)
 #define PDL_WAIT() asm volatile("griddepcontrol.wait;\n\tgriddepcontrol.launch_dependents;" ::: "memory")
 
@@ -66,10 +76,23 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                : "memory");
 }
 
-// fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-17 relative: the operand format of the tensor-core convs
+// fp32 -> (hi, lo) bf16 with hi + lo == x to ~2^-18 relative: the operand format of the tensor-core convs.
+// Rounding to bf16 is done on the bit pattern (add half an ulp of the kept part, drop the low 16 bits: round to nearest,
+// ties away from zero) instead of cvt.rn.bf16.f32: the conversion pipe runs at a quarter of the integer / FP32 rate, and
+// every tensor-core epilogue converts two values per output element (ncu/timeline: ~0.5 us of a 2.4 us epilogue).
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  const uint32_t h = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+  const float r = x - __uint_as_float(h);                 // exact
+  const uint32_t l = __float_as_uint(r) + 0x8000u;
+  hi = __ushort_as_bfloat16((unsigned short)(h >> 16));
+  lo = __ushort_as_bfloat16((unsigned short)(l >> 16));
+}
+// two values at once, packed as bf16 pairs (a in the low half): PRMT does the packing
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ha = (__float_as_uint(a) + 0x8000u) & 0xFFFF0000u, hb = (__float_as_uint(b) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t la = __float_as_uint(a - __uint_as_float(ha)) + 0x8000u, lb = __float_as_uint(b - __uint_as_float(hb)) + 0x8000u;
+  hi = __byte_perm(ha, hb, 0x7632);
+  lo = __byte_perm(la, lb, 0x7632);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -972,6 +995,12 @@ constexpr int DDS_NS = 4;      // chunk ring depth
 
 struct DdsP {
   const float* x;
+  // ConvFlow front fused into the first layer (modules.py:366-367 + DDSConv's `x = x + g`, :97-98): when x0 is set the
+  // layer's input is h[t][c] = pre_w[c] * x0[t] + pre_b[c] + cond[t][c] instead of x (same op order as the separate kernel)
+  const float* x0;
+  const float* pre_w;
+  const float* pre_b;
+  const float* cond;
   float* y;
   const float *sep_w, *sep_b, *ln1g, *ln1b, *pw_w, *pw_b, *ln2g, *ln2b;
   int C, k, dil, ldw;
@@ -1060,12 +1089,18 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
 
   float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
   const int half = (P.k - 1) / 2;
+  const float fpw = P.x0 ? P.pre_w[c] : 0.f, fpb = P.x0 ? P.pre_b[c] : 0.f;
+  auto ld_x = [&](int t) -> float {
+    const long row = base + t;
+    if (P.x0) return fmaf(fpw, P.x0[row], fpb) + P.cond[row * (long)C + c];
+    return P.x[row * (long)C + c];
+  };
 #pragma unroll
   for (int i = 0; i < DDS_TT; ++i) {
     float a = P.sep_b[c];
     for (int j = 0; j < P.k; ++j) {
       const int t = t0 + i + (j - half) * P.dil;
-      if (t >= 0 && t < len) a = fmaf(P.sep_w[j * C + c], P.x[(base + t) * (long)C + c], a);
+      if (t >= 0 && t < len) a = fmaf(P.sep_w[j * C + c], ld_x(t), a);
     }
     v[i] = a;
   }
@@ -1109,7 +1144,7 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
       const int t = t0 + i;
       if (t < len) {
         const long idx = (base + t) * (long)C + c;
-        P.y[idx] = P.x[idx] + gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
+        P.y[idx] = ld_x(t) + gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
       }
     }
   }
@@ -1244,6 +1279,7 @@ __global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, floa
   x1[row] = __fadd_rn(__fmul_rn(root, in_w), in_cw);
 }
 
+constexpr int SEQ_GAP = 8;
 // ------------------------------------------------------------------------------------------------
 // Durations (models.py:1689-1691; modules.py:296 for the ElementwiseAffine inverse):
 //   logw = (z - m) * exp(-logs);  w = exp(logw) * length_scale;  w_ceil = ceil(w);  cum = cumsum(w_ceil)
@@ -1251,7 +1287,8 @@ __global__ void spline_inverse_kernel(const float* __restrict__ h, int ldh, floa
 // ------------------------------------------------------------------------------------------------
 __global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, const float* __restrict__ prm,
                                 int* __restrict__ wceil, int* __restrict__ cum, int* __restrict__ ylen,
-                                const int* __restrict__ lens, const int* __restrict__ offs) {
+                                const int* __restrict__ lens, const int* __restrict__ offs,
+                                int* __restrict__ yoff, int B, volatile int* host_out, unsigned int* __restrict__ done_counter) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.x;
@@ -1288,12 +1325,34 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
     if (threadIdx.x == blockDim.x - 1) carry += part[threadIdx.x];
     __syncthreads();
   }
-  if (threadIdx.x == 0) ylen[b] = carry < 1 ? 1 : carry;
+  if (threadIdx.x == 0) {
+    ylen[b] = carry < 1 ? 1 : carry;
+    // the block that finishes last lays the utterances out at frame resolution and publishes lengths + offsets to the host
+    // (what frame_offsets_kernel does as a separate launch)
+    __threadfence();
+    const unsigned int ticket = atomicAdd(done_counter, 1u);
+    if (ticket == (unsigned int)B - 1u) {
+      __threadfence();
+      int o = 0;
+      for (int b2 = 0; b2 < B; ++b2) {
+        const int yl = *((volatile int*)&ylen[b2]);
+        yoff[b2] = o;
+        if (host_out) { host_out[1 + b2] = yl; host_out[1 + B + b2] = o; }
+        o += yl + (b2 + 1 < B ? SEQ_GAP : 0);
+      }
+      yoff[B] = o;
+      if (host_out) {
+        host_out[1 + 2 * B] = o;
+        __threadfence_system();
+        host_out[0] = __float_as_int(prm[6]);
+      }
+      *done_counter = 0u;
+    }
+  }
 }
 
 // Packed row offsets of the utterances at frame resolution.  SEQ_GAP empty rows separate consecutive utterances
 // (never written, zeroed where a TMA-fed kernel reads them) so that a conv halo can never reach a neighbour.
-constexpr int SEQ_GAP = 8;
 // `host_out` (optional) is pinned host memory mapped into the device address space: the lengths and offsets are
 // published there, followed by the call's sequence number (prm[6]), so the host can pick them up by polling instead
 // of paying for copy nodes plus a stream synchronisation between the two phases of a call.

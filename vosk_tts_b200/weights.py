@@ -109,8 +109,8 @@ class _Packer:
         self.chunks.append(a)
         self.pos += a.size
 
-    def conv(self, name, w, b=None, co_perm=None, ci_perm=None):
-        """w: [Co, Ci, k] (Conv1d layout)."""
+    def conv(self, name, w, b=None, co_perm=None, ci_perm=None, need_w=True):
+        """w: [Co, Ci, k] (Conv1d layout).  need_w=False: only the bias is packed (the conv runs on tcgen05 from its .th/.tl copy)."""
         w = np.asarray(w, np.float32)
         if co_perm is not None:
             w = w[co_perm]
@@ -124,7 +124,8 @@ class _Packer:
         bp = np.zeros(ldw, np.float32)
         if b is not None:
             bp[:co] = np.asarray(b, np.float32)
-        self.add(name + ".w", wp)
+        if need_w:
+            self.add(name + ".w", wp)
         self.add(name + ".b", bp)
 
     def conv_tc(self, name, w, co_perm=None, ci_perm=None):
@@ -171,10 +172,16 @@ def tc_supported(cfg):
             (cfg["upsample_initial_channel"] >> n_ups) % 64 == 0)
 
 
-def pack(w, cfg, tc=True):
+def pack(w, cfg, tc=True, precision=None):
     """w: folded state dict (reference names); returns (blob float32[n], manifest str).
-    tc=True also packs split-bf16 copies of the decoder convs for the tcgen05 path (precision mode 1)."""
-    tc = tc and tc_supported(cfg)
+    tc=True also packs split-bf16 copies of the convs for the tcgen05 path (precision modes 1 / 2).
+    precision: None packs everything (a blob any engine mode can be created from); 0 / 1 / 2 leave out the tensors that
+    mode never reads (mode 0: no split-bf16 copies at all; mode 1: none for the text encoder) -- what travels in the
+    one-time NCCL weight broadcast of a multi-GPU job."""
+    tc = tc and tc_supported(cfg) and precision != 0
+    enc_tc = tc and precision in (None, 2)
+    fw = not (tc and precision in (1, 2))      # fp32 copies of the flow / decoder convs (the tcgen05 modes read only .th/.tl + bias)
+    ew = not (tc and precision == 2)           # ... of the text encoder's convs
     g = lambda k: w[k].detach().cpu().numpy() if hasattr(w[k], "detach") else np.asarray(w[k])
     H, I, G = cfg["hidden_channels"], cfg["inter_channels"], cfg["gin_channels"]
     D = cfg["dp_filter_channels"]
@@ -184,12 +191,12 @@ def pack(w, cfg, tc=True):
         P.add(dst + ".g", g(src + ".gamma"))
         P.add(dst + ".b", g(src + ".beta"))
 
-    def enc_layer(dst, src, i, with_tc=False):
+    def enc_layer(dst, src, i, with_tc=False, need_w=True):
         a = "%s.attn_layers.%d" % (src, i)
         wq = np.concatenate([g(a + ".conv_q.weight"), g(a + ".conv_k.weight"), g(a + ".conv_v.weight")], 0)
         bq = np.concatenate([g(a + ".conv_q.bias"), g(a + ".conv_k.bias"), g(a + ".conv_v.bias")], 0)
-        P.conv(dst + ".qkv", wq, bq)
-        P.conv(dst + ".o", g(a + ".conv_o.weight"), g(a + ".conv_o.bias"))
+        P.conv(dst + ".qkv", wq, bq, need_w=need_w)
+        P.conv(dst + ".o", g(a + ".conv_o.weight"), g(a + ".conv_o.bias"), need_w=need_w)
         if with_tc:
             f_ = "%s.ffn_layers.%d" % (src, i)
             P.conv_tc(dst + ".qkv", wq)
@@ -212,8 +219,8 @@ def pack(w, cfg, tc=True):
                     P.add(dst + nm + "l", lo.reshape(-1).view(np.float32))
         ln(dst + ".ln1", "%s.norm_layers_1.%d" % (src, i))
         f = "%s.ffn_layers.%d" % (src, i)
-        P.conv(dst + ".ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"))
-        P.conv(dst + ".ffn2", g(f + ".conv_2.weight"), g(f + ".conv_2.bias"))
+        P.conv(dst + ".ffn1", g(f + ".conv_1.weight"), g(f + ".conv_1.bias"), need_w=need_w)
+        P.conv(dst + ".ffn2", g(f + ".conv_2.weight"), g(f + ".conv_2.bias"), need_w=need_w)
         ln(dst + ".ln2", "%s.norm_layers_2.%d" % (src, i))
 
     def dds(dst, src, n_layers=3):
@@ -251,9 +258,9 @@ def pack(w, cfg, tc=True):
     # ---- text encoder
     P.add("enc.emb", g("enc_p.emb.weight"))
     for i in range(cfg["n_layers"]):
-        enc_layer("enc.%d" % i, "enc_p.encoder", i, with_tc=tc)
-    P.conv("enc.proj", g("enc_p.proj.weight"), g("enc_p.proj.bias"))
-    if tc:
+        enc_layer("enc.%d" % i, "enc_p.encoder", i, with_tc=enc_tc, need_w=ew)
+    P.conv("enc.proj", g("enc_p.proj.weight"), g("enc_p.proj.bias"), need_w=ew)
+    if enc_tc:
         P.conv_tc("enc.proj", g("enc_p.proj.weight"))
 
     # ---- stochastic duration predictor
@@ -278,26 +285,26 @@ def pack(w, cfg, tc=True):
         flipped = ((nf - f) % 2) == 1
         P.conv(dst + ".pre", g(src + ".pre.weight"), g(src + ".pre.bias"), ci_perm=rev if flipped else None)
         if cfg["use_transformer_flows"]:
-            enc_layer(dst + ".tr", src + ".pre_transformer", 0, with_tc=tc)
+            enc_layer(dst + ".tr", src + ".pre_transformer", 0, with_tc=tc, need_w=fw)
         nl = cfg["flow_wn_layers"]
         il = np.arange(2 * H).reshape(2, H).T.reshape(-1)
         for i in range(nl):
             P.conv("%s.in%d" % (dst, i), g("%s.enc.in_layers.%d.weight" % (src, i)),
-                   g("%s.enc.in_layers.%d.bias" % (src, i)), co_perm=il)
+                   g("%s.enc.in_layers.%d.bias" % (src, i)), co_perm=il, need_w=fw)
             rw, rb = g("%s.enc.res_skip_layers.%d.weight" % (src, i)), g("%s.enc.res_skip_layers.%d.bias" % (src, i))
             if tc:
                 P.conv_tc("%s.in%d" % (dst, i), g("%s.enc.in_layers.%d.weight" % (src, i)), co_perm=il)
             if i < nl - 1:
-                P.conv("%s.rsx%d" % (dst, i), rw[:H], rb[:H])
-                P.conv("%s.rss%d" % (dst, i), rw[H:], rb[H:])
+                P.conv("%s.rsx%d" % (dst, i), rw[:H], rb[:H], need_w=fw)
+                P.conv("%s.rss%d" % (dst, i), rw[H:], rb[H:], need_w=fw)
                 if tc:
                     P.conv_tc("%s.rsx%d" % (dst, i), rw[:H])
                     P.conv_tc("%s.rss%d" % (dst, i), rw[H:])
             else:
-                P.conv("%s.rss%d" % (dst, i), rw, rb)
+                P.conv("%s.rss%d" % (dst, i), rw, rb, need_w=fw)
                 if tc:
                     P.conv_tc("%s.rss%d" % (dst, i), rw)
-        P.conv(dst + ".post", g(src + ".post.weight"), g(src + ".post.bias"), co_perm=rev if flipped else None)
+        P.conv(dst + ".post", g(src + ".post.weight"), g(src + ".post.bias"), co_perm=rev if flipped else None, need_w=fw)
         if tc:
             P.conv_tc(dst + ".post", g(src + ".post.weight"), co_perm=rev if flipped else None)
 
@@ -305,7 +312,7 @@ def pack(w, cfg, tc=True):
     pre_w = g("dec.conv_pre.weight")
     if nf % 2 == 1:   # odd number of flips leaves the latent channel-reversed: fold into conv_pre
         pre_w = pre_w[:, ::-1].copy()
-    P.conv("dec.pre", pre_w, g("dec.conv_pre.bias"))
+    P.conv("dec.pre", pre_w, g("dec.conv_pre.bias"), need_w=fw)
     if tc:
         P.conv_tc("dec.pre", pre_w)
     nk = len(cfg["resblock_kernel_sizes"])
@@ -314,7 +321,7 @@ def pack(w, cfg, tc=True):
         bt = g("dec.ups.%d.bias" % i)
         for r, (pad, js) in enumerate(convt_phases(u, ku)):
             wr = np.stack([wt[:, :, j] for j in js], axis=-1)   # [Cin, Cout, ntaps]
-            P.conv("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)), bt)
+            P.conv("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)), bt, need_w=fw)
             if tc:
                 P.conv_tc("dec.up%d.p%d" % (i, r), np.transpose(wr, (1, 0, 2)))
         for j in range(nk):
@@ -322,8 +329,8 @@ def pack(w, cfg, tc=True):
             nd = len(cfg["resblock_dilation_sizes"][j])
             for d in range(nd):
                 if cfg["resblock"] == "1":
-                    P.conv("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)), g("dec.resblocks.%d.convs1.%d.bias" % (n, d)))
-                    P.conv("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)), g("dec.resblocks.%d.convs2.%d.bias" % (n, d)))
+                    P.conv("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)), g("dec.resblocks.%d.convs1.%d.bias" % (n, d)), need_w=fw)
+                    P.conv("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)), g("dec.resblocks.%d.convs2.%d.bias" % (n, d)), need_w=fw)
                     if tc:
                         P.conv_tc("dec.rb%d.c1.%d" % (n, d), g("dec.resblocks.%d.convs1.%d.weight" % (n, d)))
                         P.conv_tc("dec.rb%d.c2.%d" % (n, d), g("dec.resblocks.%d.convs2.%d.weight" % (n, d)))
@@ -335,7 +342,7 @@ def pack(w, cfg, tc=True):
         # multistream_conv_post (models.py:1107), or -- one band, nothing after the iSTFT (models.py:962-965) -- a unit impulse.
         post = "dec.conv_post" if cfg["decoder"] == "istft" else "dec.subband_conv_post"
         post_b = g(post + ".bias") if (post + ".bias") in w else None          # only the multistream decoder has one (:1095)
-        P.conv("dec.post", g(post + ".weight"), post_b)
+        P.conv("dec.post", g(post + ".weight"), post_b, need_w=fw)
         if tc:
             P.conv_tc("dec.post", g(post + ".weight"))
         P.add("dec.istft", istft_inverse_basis(cfg["gen_istft_n_fft"], cfg["gen_istft_hop_size"]))
