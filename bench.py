@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=5)
-    ap.add_argument("--precision", type=int, default=1, help="0: fp32 FFMA everywhere; 1: flow+decoder on tcgen05 (split-bf16 x3); 2: encoder too")
+    ap.add_argument("--precision", type=int, default=1, help="0: fp32 FFMA everywhere; 1: flow+decoder on tcgen05 (split-bf16 x3); 2: encoder too; 3: encoder on tcgen05 with the exact 3-way split")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (configs[2], configs[4], fp32-exact mode)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -590,7 +590,8 @@ def main():
                         "h2d_bytes_per_step": int(wl["tok"].nbytes + 16 + 8 + wl["eps_dp"].nbytes + wl["eps_z"][:, :, :Ty].nbytes),
                         "d2h_bytes_per_step": int(n_samples * 4 + 8)},
                 "e2e_cold": {"value": cold_n_all / cold_total, "unit": "samples/s", "utterances": 20 * world,
-                             "ms_per_utterance": 1e3 * cold_total / 20, "phonemes": "100..128 (uniform), random speaker, engine-drawn noise",
+                             "ms_per_utterance": 1e3 * cold_total / 20, "ms_median_min_max_rank0": [1e3 * sorted(cold_t)[10], 1e3 * min(cold_t), 1e3 * max(cold_t)],
+                             "phonemes": "100..128 (uniform), random speaker, engine-drawn noise",
                              "graph_replays_in_timed_region": r2 - r1, "graph_launches_expected": 40,
                              "speculation_hits_misses": [h2 - h1, m2 - m1],
                              "warmup": "40 OTHER distinct utterances of the same distribution (rank 0: %d graph replays among them; the first "

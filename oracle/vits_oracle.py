@@ -421,7 +421,7 @@ def decoder_hifigan(z, w, cfg, g=None):
 
 
 # --------------------------------------------------------------------------- the whole path
-def infer(w, cfg, tokens, lengths, sid, scales, eps_dp, eps_z=None, return_all=False):
+def infer(w, cfg, tokens, lengths, sid, scales, eps_dp, eps_z=None, return_all=False, decode=True):
     """SynthesizerTrn.infer (models.py:1679-1704).
 
     scales = [noise_scale, length_scale, noise_scale_w] (onnx_export.py:61-64).
@@ -446,6 +446,8 @@ def infer(w, cfg, tokens, lengths, sid, scales, eps_dp, eps_z=None, return_all=F
         e = eps_z[:, :, :Ty]
     z_p = m_e + e * torch.exp(logs_e) * noise_scale
     z = flow_reverse(z_p, y_mask, g, w, cfg)
+    if not decode:      # (long utterances: the caller vocodes slices of z itself, the decoder being local -- +-24 frames)
+        return dict(w_ceil=w_ceil, y_lengths=y_lengths, idx=idx, logw=logw, z_p=z_p, z=z, y_mask=y_mask, g=g)
     zin = z * y_mask
     if cfg["decoder"] in ("mb_istft", "ms_istft", "istft"):
         o, o_mb = decoder_mb_istft(zin, w, cfg)

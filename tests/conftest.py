@@ -40,9 +40,10 @@ def packed(folded, cfg):
     return weights.pack(folded, cfg)
 
 
-@pytest.fixture(scope="session", params=[0, 1, 2], ids=["fp32-ffma", "tcgen05-flow-decoder", "tcgen05-all"])
+@pytest.fixture(scope="session", params=[0, 1, 2, 3], ids=["fp32-ffma", "tcgen05-flow-decoder", "tcgen05-all", "tcgen05-all-exact-encoder"])
 def engine(request, packed, cfg):
-    """precision 0: fp32 FFMA kernels everywhere; precision 1: flow + decoder convs on tcgen05 (split-bf16 x3)."""
+    """precision 0: fp32 FFMA kernels everywhere; 1: flow + decoder convs (and batched attention) on tcgen05 (split-bf16, 3 MMAs
+    per K16 slice); 2: text encoder too; 3: text encoder on tcgen05 with the exact 3-way split (6 MMAs per K16 slice)."""
     import torch
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

@@ -39,7 +39,7 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     n_full = int(sys.argv[2]) if len(sys.argv) > 2 else 100
     out_path = sys.argv[3] if len(sys.argv) > 3 else None
-    modes = [int(m) for m in os.environ.get("SWEEP_MODES", "0,1,2").split(",")]
+    modes = [int(m) for m in os.environ.get("SWEEP_MODES", "0,1,2,3").split(",")]
     cfg = C.DEFAULT_CONFIG
     w = weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234))
     blob, man = weights.pack(w, cfg)

@@ -1,7 +1,6 @@
 """the other inverse-STFT decoders of the reference (Multistream_iSTFT_Generator,
 iSTFT_Generator).  The oracle restatement and the weight packing are pinned against the UNMODIFIED reference on CPU
-(build container only).  The CUDA engine still refuses these variants: its tail kernel has not had a GPU parity run
-with a learned / single-band filter yet (engine.py raises NotImplementedError), so there is no `-m gpu` test here."""
+(build container only); the CUDA engine's parity run for them is tests/test_gpu_parity.py::test_istft_decoder_variants_vs_oracle."""
 import copy
 
 import numpy as np
@@ -74,11 +73,14 @@ def test_packed_tail_filter_is_what_the_decoder_applies(flag):
         assert bank.shape == (1, 63) and bank[0, 31] == 1.0 and np.count_nonzero(bank) == 1
 
 
-def test_engine_refuses_unvalidated_variants():
+def test_engine_config_accepts_every_istft_decoder():
+    """All three inverse-STFT decoders map onto the same engine decoder type (the tail kernel takes the filter bank from
+    the blob); the GPU parity runs are tests/test_gpu_parity.py::test_istft_decoder_variants_vs_oracle."""
     from vosk_tts_b200 import engine
-    cfg = C.from_training_json(_training_json("ms_istft_vits"), n_vocab=N_VOCAB)
-    with pytest.raises(NotImplementedError):
-        engine.make_c_config(cfg)
+    for flag in ("ms_istft_vits", "istft_vits", "mb_istft_vits"):
+        cfg = C.from_training_json(_training_json(flag), n_vocab=N_VOCAB)
+        cc = engine.make_c_config(cfg)
+        assert cc.decoder_type == 0 and cc.subbands == (1 if flag == "istft_vits" else 4)
 
 
 @pytest.mark.parametrize("flag,kind", [("ms_istft_vits", "ms_istft"), ("istft_vits", "istft")])

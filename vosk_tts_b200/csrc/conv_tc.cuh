@@ -45,6 +45,8 @@ enum : int { TCE_RELU = 1, TCE_GATE = 2 };
 
 struct TcProblem {
   CUtensorMap a_hi, a_lo, w_hi, w_lo;
+  CUtensorMap a_mid, w_mid;   // third planes of the exact 3-way split (TcBatch::np == 3)
+  __nv_bfloat16* p_mid;       // third output plane (or null)
   const float* bias;
   const float* cond;          // per-utterance vector added before the activation (or null)
   const float* res;           // fp32 residual added to the fp32 output (or null)
@@ -69,6 +71,9 @@ struct TcBatch {
   int baseoff;  // experiment: fill the descriptor base-offset field for row-shifted tiles
   int cn;       // CTAs of a cluster along the channel-tile axis that share (TMA-multicast) one activation tile; 1 = off
   int wpre;     // 1: request the first ring of weight tiles before the dependency wait (latency-bound single-wave launches)
+  int np;       // operand planes: 2 = (hi, lo), three MMAs per K16 slice (lo*hi + hi*lo + hi*hi, ~2^-17 relative);
+                //   3 = (hi, mid, lo), six MMAs (hl + lh + mm + mh + hm + hh): products exact to the last fp32 bit
+  int ast, wst; // ring depths (activation / weight tiles) for this launch
   int split;    // cluster split-K: `split` CTAs (cluster dims (1,1,split)) each run a contiguous range of the k-steps of one
                 //    output tile, exchange partial accumulators through distributed shared memory and each finish
                 //    64/split of the tile's columns (reduce-scatter; fixed summation order => deterministic).  1 = off
@@ -209,12 +214,29 @@ __device__ __forceinline__ void tc_finish_cols(const TcProblem& P, float (&v)[EN
     const bool al = ((P.ldp | P.poff) & 7) == 0;
 #pragma unroll
     for (int i = 0; i < EN; i += 8) {
-      __align__(16) __nv_bfloat16 hb[8], lb[8];
+      __align__(16) __nv_bfloat16 hb[8], lb[8], mb[8];
+      if (P.p_mid) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        float u = v[i + e];
-        u = u > 0.f ? u : u * P.pl_slope;
-        split_bf16(u, hb[e], lb[e]);
+        for (int e = 0; e < 8; ++e) {
+          float u = v[i + e];
+          u = u > 0.f ? u : u * P.pl_slope;
+          split_bf16_3(u, hb[e], mb[e], lb[e]);
+        }
+        __nv_bfloat16* pm = P.p_mid + orow * (long)P.ldp + P.poff + ocb;
+        if (al && i + 8 <= nvalid) {
+          *reinterpret_cast<uint4*>(pm + i) = *reinterpret_cast<const uint4*>(mb);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (i + e < nvalid) pm[i + e] = mb[e];
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float u = v[i + e];
+          u = u > 0.f ? u : u * P.pl_slope;
+          split_bf16(u, hb[e], lb[e]);
+        }
       }
       if (al && i + 8 <= nvalid) {
         *reinterpret_cast<uint4*>(ph + i) = *reinterpret_cast<const uint4*>(hb);
@@ -286,15 +308,16 @@ __device__ __forceinline__ void tc_split_tail(const TcProblem& P, LoadAcc&& load
 }
 
 template <int BN>
-constexpr int tc_smem_bytes(int a_bytes) {
-  return tc_ast<BN>() * 2 * a_bytes + tc_wst<BN>() * 2 * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+constexpr int tc_smem_bytes(int a_bytes, int np = 2, int ast = tc_ast<BN>(), int wst = tc_wst<BN>()) {
+  return ast * np * a_bytes + wst * np * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 }
+constexpr int TC_MAXST = 4;   // barrier slots per ring
 
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
   constexpr int B_BYTES = BN * TC_BK * 2;
-  constexpr int TC_AST = tc_ast<BN>(), TC_WST = tc_wst<BN>();
+  const int TC_AST = tb.ast, TC_WST = tb.wst, NP = tb.np;
   PDL_LAUNCH();
   if (threadIdx.x == 0) TC_STAMP(0);
   // cluster split-K ways; blockIdx.z = (b * n + problem) * S + rank.  The non-split instantiation carries none of the
@@ -312,12 +335,12 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
 
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_w = smem + TC_AST * 2 * A_BYTES;
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_w + TC_WST * 2 * B_BYTES);
-  uint64_t* a_empty = a_full + TC_AST;
-  uint64_t* w_full = a_empty + TC_AST;
-  uint64_t* w_empty = w_full + TC_WST;
-  uint64_t* tmem_full = w_empty + TC_WST;
+  uint8_t* smem_w = smem + TC_AST * NP * A_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem_w + TC_WST * NP * B_BYTES);
+  uint64_t* a_empty = a_full + TC_MAXST;
+  uint64_t* w_full = a_empty + TC_MAXST;
+  uint64_t* w_empty = w_full + TC_MAXST;
+  uint64_t* tmem_full = w_empty + TC_MAXST;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
 
@@ -335,6 +358,10 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_lo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_lo)) : "memory");
+    if (NP == 3) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_mid)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_mid)) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
@@ -357,10 +384,11 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   auto issue_w = [&](int s) {
     const int c = s / P.k, j = s - c * P.k;
     const int wst = (s - s_beg) % TC_WST;
-    uint8_t* wb = smem_w + wst * 2 * B_BYTES;
-    mbar_expect_tx(&w_full[wst], 2 * B_BYTES);
+    uint8_t* wb = smem_w + wst * NP * B_BYTES;
+    mbar_expect_tx(&w_full[wst], NP * B_BYTES);
     tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
+    if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
   };
   if (warp == 0 && lane == 0)
     for (int i = 0; i < w_pre; ++i) issue_w(s_beg + i);
@@ -379,14 +407,14 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      const uint32_t a_tx = 2u * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per tile pair
+      const uint32_t a_tx = (uint32_t)NP * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per set of planes
       for (int s = s_beg; s < s_end; ++s) {
         const int c = s / P.k, j = s - c * P.k;
         const int ls = s - s_beg;                              // ring positions count this CTA's own steps
         if (ls % a_per == 0) {
           const int ai = ls / a_per, ast = ai % TC_AST, use = ai / TC_AST;
           if (use > 0) mbar_wait(&a_empty[ast], (use - 1) & 1);
-          uint8_t* ab = smem + ast * 2 * A_BYTES;
+          uint8_t* ab = smem + ast * NP * A_BYTES;
           mbar_expect_tx(&a_full[ast], a_tx);
           const int row = (int)in_base + t0 - P.pad + (tall ? 0 : j * P.dil);
           if (cn > 1) {
@@ -398,6 +426,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           } else {
             tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
             tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
+            if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]);
           }
         }
         if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
@@ -422,16 +451,31 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         mbar_wait(&w_full[wst], (ls / TC_WST) & 1);
         if (ls == 0) TC_STAMP(4);
         tc_fence_after();
-        const uint32_t abase = smem_u32(smem + ast * 2 * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
-        const uint32_t wbase = smem_u32(smem_w + wst * 2 * B_BYTES);
+        const uint32_t abase = smem_u32(smem + ast * NP * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
+        const uint32_t wbase = smem_u32(smem_w + wst * NP * B_BYTES);
         const uint64_t ahi = umma_desc_sw128(abase, tb.baseoff), alo = umma_desc_sw128(abase + A_BYTES, tb.baseoff);
         const uint64_t bhi = umma_desc_sw128(wbase), blo = umma_desc_sw128(wbase + B_BYTES);
+        if (NP == 3) {
+          // exact 3-way split: the six products that reach the last bit of an fp32 product, smallest first
+          const uint64_t ami = umma_desc_sw128(abase + 2 * A_BYTES), bmi = umma_desc_sw128(wbase + 2 * B_BYTES);
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 16; ++kk) {
-          const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
-          umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (ls | kk) ? 1u : 0u);
-          umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
-          umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+            umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, (ls | kk) ? 1u : 0u);
+            umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
+            umma_bf16(tmem_base, ami + adv, bmi + adv, idesc, 1u);
+            umma_bf16(tmem_base, ami + adv, bhi + adv, idesc, 1u);
+            umma_bf16(tmem_base, ahi + adv, bmi + adv, idesc, 1u);
+            umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
+          }
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
+            umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (ls | kk) ? 1u : 0u);
+            umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
+            umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
+          }
         }
         umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
         if ((ls + 1) % a_per == 0) {                           // ... and the activation tile after its last tap

@@ -44,10 +44,12 @@ struct ConvW {
 struct TcW {     // split-bf16 copy of a conv weight: [k][Cout][Cin]
   const __nv_bfloat16* hi = nullptr;
   const __nv_bfloat16* lo = nullptr;
+  const __nv_bfloat16* mid = nullptr;   // third plane of the exact 3-way split (precision mode 3, text encoder)
 };
 struct Planes {  // split-bf16 activation planes [rows][C]
   __nv_bfloat16* hi = nullptr;
   __nv_bfloat16* lo = nullptr;
+  __nv_bfloat16* mid = nullptr;         // third plane (exact 3-way split) or null
   int C = 0;
   long rows = 0;
 };
@@ -166,7 +168,8 @@ struct vtts_engine {
   int hop = 0, up_total = 1;
   bool tc = false;                      // precision mode 1: tcgen05 path for the decoder convs
   TcW tc_pre, tc_post, tc_encproj;
-  bool enc_on_tc = false;               // precision mode 2: the text encoder's convs on tcgen05 as well
+  bool enc_on_tc = false;               // precision modes 2 / 3: the text encoder's convs on tcgen05 as well
+  bool enc_three = false;               // mode 3: with the exact 3-way operand split
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -200,7 +203,9 @@ struct vtts_engine {
   float spec_ratio = 0.f;
   uint64_t spec_hits = 0, spec_misses = 0;
   double spec_units() const { return (double)real_maxTok * (double)std::max(0.05f, scales[1]); }
-  int spec_predict() const { return (int)std::ceil((double)spec_ratio * 1.08 * spec_units()) + 8; }
+  int spec_cap = 0;                   // length bucket of the speculative second phase of the current call (0: not speculating)
+  float spec_margin = 1.08f;
+  int spec_predict() const { return (int)std::ceil((double)spec_ratio * spec_margin * spec_units()) + 8; }
   void spec_learn() {
     spec_hist[spec_n++ % 16] = (float)((double)real_maxFrm / spec_units());
     float m = 0.f;
@@ -264,7 +269,7 @@ struct vtts_engine {
   std::vector<int> h_tok_len, h_tok_off, h_frm_len, h_frm_off;
 
   // ---- workspace
-  Buf<int> d_ids, d_tok_len, d_tok_off, d_sid, d_wceil, d_cum, d_frm_len, d_frm_off, d_ftok, d_done_ctr;
+  Buf<int> d_ids, d_tok_len, d_tok_off, d_sid, d_wceil, d_cum, d_frm_len, d_frm_off, d_ftok, d_done_ctr, d_frm_len_real;
   Buf<float> d_condv, d_x, d_xb, d_qkv, d_ao, d_y, d_ffh, d_stats, d_dA, d_dB, d_dx, d_h29, d_za, d_zb, d_eps_dp;
   Buf<float> d_z, d_h, d_h1, d_wx, d_acts, d_skip, d_fqkv, d_fao, d_fy, d_ffh2, d_eps_z, d_d0, d_post, d_wav;
   std::vector<Buf<float>> d_stage;               // X_i
@@ -470,15 +475,17 @@ struct vtts_engine {
     L.rv_hi = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rvh", 16 * 128 / 2));
     L.rv_lo = reinterpret_cast<const __nv_bfloat16*>(vec(p + ".rvl", 16 * 128 / 2));
   }
-  TcW tcw(const std::string& name, int Cin, int Cout, int k) {
+  TcW tcw(const std::string& name, int Cin, int Cout, int k, bool three = false) {
     TcW t;
     const size_t n = (size_t)k * Cout * Cin / 2;
-    t.hi = reinterpret_cast<const __nv_bfloat16*>(vec(name + ".th", n));
-    t.lo = reinterpret_cast<const __nv_bfloat16*>(vec(name + ".tl", n));
+    t.hi = reinterpret_cast<const __nv_bfloat16*>(vec(name + (three ? ".t3h" : ".th"), n));
+    t.lo = reinterpret_cast<const __nv_bfloat16*>(vec(name + (three ? ".t3l" : ".tl"), n));
+    if (three) t.mid = reinterpret_cast<const __nv_bfloat16*>(vec(name + ".t3m", n));
     REQUIRE(Cin % TC_BK == 0, VTTS_ERR_INVALID, "tensor-core conv needs input channels in multiples of 64");
     return t;
   }
-  Planes planes(int slot, long units, int rm, int C, int extra = 0) {
+  Buf<__nv_bfloat16> pl_pool_mid[64];
+  Planes planes(int slot, long units, int rm, int C, int extra = 0, bool three = false) {
     Planes p;
     const long rows = units * rm + (extra ? (long)B * extra : 0);
     p.C = C; p.rows = rows;
@@ -491,10 +498,15 @@ struct vtts_engine {
     // tile) are multiplied by exact zeros in the attention's P V product, so they must at least be finite
     if (pl_pool[2 * slot].cap != cap_hi) CK(cudaMemsetAsync(p.hi, 0, pl_pool[2 * slot].cap * sizeof(__nv_bfloat16), stream));
     if (pl_pool[2 * slot + 1].cap != cap_lo) CK(cudaMemsetAsync(p.lo, 0, pl_pool[2 * slot + 1].cap * sizeof(__nv_bfloat16), stream));
+    if (three) {
+      const size_t cap_mid = pl_pool_mid[slot].cap;
+      p.mid = ensure(pl_pool_mid[slot], n);
+      if (pl_pool_mid[slot].cap != cap_mid) CK(cudaMemsetAsync(p.mid, 0, pl_pool_mid[slot].cap * sizeof(__nv_bfloat16), stream));
+    }
     if (collecting) {   // rows behind each utterance must read as zero through TMA: zeroed by one zero_tails launch per phase
       REQUIRE(tail.n < ZT_MAXP && C % 8 == 0, VTTS_ERR_INVALID, "too many plane buffers in one phase");
       TailList::E& e = tail.e[tail.n++];
-      e.hi = p.hi; e.lo = p.lo; e.C = C; e.rm = rm; e.extra = extra; e.rows_cap = (int)rows;
+      e.hi = p.hi; e.lo = p.lo; e.mid = p.mid; e.C = C; e.rm = rm; e.extra = extra; e.rows_cap = (int)rows;
     }
     return p;
   }
@@ -555,7 +567,7 @@ ConvP mk(const ConvW& W, const float* x, int ldx, int xoff, float* y, int ldy, i
 // tcgen05 are skipped, and so are the bf16 `.th/.tl` copies of convs that stay on the FFMA pipe.)
 void vtts_engine::build_prefetch_list() {
   auto on_tc = [&](const std::string& nm) {
-    if (nm.rfind("enc.", 0) == 0) return cfg.precision == 2;
+    if (nm.rfind("enc.", 0) == 0) return cfg.precision >= 2;
     if (nm.rfind("flow.", 0) == 0 || nm.rfind("dec.", 0) == 0) return cfg.precision >= 1;
     return false;
   };
@@ -610,19 +622,20 @@ void vtts_engine::bind_weights() {
   }
   enc_emb = vec("enc.emb", (size_t)c.n_vocab * H);
   enc.clear();
-  enc_on_tc = c.precision == 2 && H % TC_BK == 0 && c.filter_channels % TC_BK == 0;
+  enc_on_tc = c.precision >= 2 && H % TC_BK == 0 && c.filter_channels % TC_BK == 0;
+  enc_three = enc_on_tc && c.precision == 3;     // exact 3-way split: durations as exact as the fp32 FFMA path
   for (int i = 0; i < c.n_layers; ++i) enc.push_back(enc_layer("enc." + std::to_string(i), H, c.filter_channels, c.kernel_size, c.n_heads, !enc_on_tc));
   enc_proj = conv("enc.proj", H, 2 * I, 1, !enc_on_tc);
   if (enc_on_tc) {
     for (int i = 0; i < c.n_layers; ++i) {
       const std::string p = "enc." + std::to_string(i);
-      enc[i].t_qkv = tcw(p + ".qkv", H, 3 * H, 1);
-      enc[i].t_o = tcw(p + ".o", H, H, 1);
-      enc[i].t_ffn1 = tcw(p + ".ffn1", H, c.filter_channels, c.kernel_size);
-      enc[i].t_ffn2 = tcw(p + ".ffn2", c.filter_channels, H, c.kernel_size);
-      bind_rel_tc(enc[i], p);
+      enc[i].t_qkv = tcw(p + ".qkv", H, 3 * H, 1, enc_three);
+      enc[i].t_o = tcw(p + ".o", H, H, 1, enc_three);
+      enc[i].t_ffn1 = tcw(p + ".ffn1", H, c.filter_channels, c.kernel_size, enc_three);
+      enc[i].t_ffn2 = tcw(p + ".ffn2", c.filter_channels, H, c.kernel_size, enc_three);
+      if (!enc_three) bind_rel_tc(enc[i], p);      // (mode 3 keeps the encoder's attention on the fp32 pipe)
     }
-    tc_encproj = tcw("enc.proj", H, 2 * I, 1);
+    tc_encproj = tcw("enc.proj", H, 2 * I, 1, enc_three);
   }
   dp_pre = conv("dp.pre", H, D, 1);
   dp_proj = conv("dp.proj", D, D, 1);
@@ -669,7 +682,7 @@ void vtts_engine::bind_weights() {
     }
     flow.push_back(F);
   }
-  tc = c.precision == 1 || c.precision == 2;
+  tc = c.precision >= 1 && c.precision <= 3;
   dec_pre = conv("dec.pre", I, c.upsample_initial_channel, 7, !tc);
   if (tc) {
     REQUIRE(c.decoder_type == 0 && c.resblock_type == 1, VTTS_ERR_INVALID, "tensor-core mode supports the MB-iSTFT / ResBlock1 decoder");
@@ -766,7 +779,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     maxNR = std::max(maxNR, nr);
   }
   if (BN == 128) tall = false;             // the 128-wide weight ring leaves no room for tall activation tiles
-  if (tall && tc_smem_bytes<64>((maxNR * 128 + 1023) / 1024 * 1024) > 227 * 1024) tall = false;
+  if (tall && tc_smem_bytes<64>((maxNR * 128 + 1023) / 1024 * 1024) > 227 * 1024) tall = false;   // (2-plane rings)
   if (!tall) maxNR = TC_BM;
   // TMA multicast of the activation tile across the channel-tile CTAs of a cluster: only when every problem of the
   // launch has the same number of channel tiles (no CTA of a cluster may drop out) and the tile is not "tall"
@@ -812,6 +825,16 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     }
   }
   if (split > 1) cn = 1;
+  int np = 0;
+  for (const TcSpec& q : ps) {
+    const int n = (q.w.mid && q.in.mid) ? 3 : 2;
+    REQUIRE(np == 0 || np == n, VTTS_ERR_INVALID, "grouped tensor-core conv mixes 2- and 3-plane problems");
+    np = n;
+  }
+  if (np == 3) { tall = false; cn = 1; }
+  tb.np = np;
+  tb.ast = np == 3 ? 2 : (BN == 128 ? tc_ast<128>() : tc_ast<64>());
+  tb.wst = np == 3 ? (BN == 128 ? 2 : 3) : (BN == 128 ? tc_wst<128>() : tc_wst<64>());
   tb.split = split;
   tb.cn = cn;
   tb.tall = tall ? 1 : 0;
@@ -825,6 +848,11 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, box_rows);
     P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
     P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN);
+    if (np == 3) {
+      P.a_mid = make_map(q.in.mid, q.in.C, q.in.rows, box_rows);
+      P.w_mid = make_map(q.w.mid, q.Cin, (long)q.k * q.Cout, BN);
+    }
+    P.p_mid = q.out.mid;
     P.bias = q.bias;
     P.res = q.res; P.ldr = q.ldr; P.roff = q.roff;
     P.y = q.y; P.ldy = q.ldy; P.yoff = q.yoff;
@@ -859,7 +887,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = grid; lc.blockDim = dim3(TC_THREADS); lc.stream = stream;
-    lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes) : tc_smem_bytes<64>(tb.a_bytes);
+    lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes, tb.np, tb.ast, tb.wst) : tc_smem_bytes<64>(tb.a_bytes, tb.np, tb.ast, tb.wst);
     cudaLaunchAttribute at[2];
     int na = 0;
     if (cn > 1 || split > 1) {
@@ -946,6 +974,7 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
   const int dk = Hc / n_heads, nrel = 2 * cfg.window_size + 1;
   __nv_bfloat16* ph = pl ? pl->hi : nullptr;
   __nv_bfloat16* plo = pl ? pl->lo : nullptr;
+  __nv_bfloat16* pmi = pl ? pl->mid : nullptr;
   // register-blocked variant (4 query rows per warp) once the launch is throughput bound
   const std::vector<int>& hl = (lens == d_tok_len.p) ? v_tok_len : v_frm_len;
   long rows = 0;
@@ -959,7 +988,7 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
     if (attn_split && R == 1 && mt <= ATS_MAXT && ctas <= 148 && dk % 32 == 0 && dk <= 128) {
       dim3 grid((maxLen + ATS_ROWS - 1) / ATS_ROWS, n_heads, B);
       const size_t smem = (size_t)attn_split_smem_floats(dk, nrel, mt) * sizeof(float);
-#define ATTN_SPLIT(D) klaunch(attn_split_kernel<D>, grid, dim3(ATS_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, mt, lens, offs, ph, plo)
+#define ATTN_SPLIT(D) klaunch(attn_split_kernel<D>, grid, dim3(ATS_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, mt, lens, offs, ph, plo, pmi)
       switch (dk / 32) { case 1: ATTN_SPLIT(1); break; case 2: ATTN_SPLIT(2); break; case 3: ATTN_SPLIT(3); break; default: ATTN_SPLIT(4); break; }
 #undef ATTN_SPLIT
       CK(cudaGetLastError());
@@ -970,7 +999,7 @@ void vtts_engine::launch_attn(const float* qkv, float* ao, const EncLayerW& L, i
   const int QT = 8 * R;
   dim3 grid((maxLen + QT - 1) / QT, n_heads, B);
   const size_t smem = (size_t)attn_smem_floats(dk, nrel, R) * sizeof(float);
-#define ATTN_CASE(D, RR) klaunch(attn_kernel<D, RR>, grid, dim3(AT_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, lens, offs, ph, plo)
+#define ATTN_CASE(D, RR) klaunch(attn_kernel<D, RR>, grid, dim3(AT_THREADS), smem, qkv, 3 * Hc, ao, Hc, L.relk, L.relv, n_heads, cfg.window_size, lens, offs, ph, plo, pmi)
   if (R == 4) {
     switch (dk / 32) { case 1: ATTN_CASE(1, 4); break; case 2: ATTN_CASE(2, 4); break; case 3: ATTN_CASE(3, 4); break; default: ATTN_CASE(4, 4); break; }
   } else {
@@ -1052,7 +1081,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo, bool emit_pz) 
       }
       { TcSpec q; q.in = pao; q.w = W.t_o; q.bias = W.tr.o.b; q.Cin = H; q.Cout = H; q.y = fy; q.ldy = H;
         launch_tc({q}, 1, fl, fo, maxFrm, B); }
-      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, h1, fl, fo, H, ph1.hi, ph1.lo, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       { TcSpec q; q.in = ph1; q.w = W.t_ffn1; q.bias = W.tr.ffn1.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
@@ -1061,7 +1090,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo, bool emit_pz) 
       { TcSpec q; q.in = pff; q.w = W.t_ffn2; q.bias = W.tr.ffn2.b; q.Cin = H; q.Cout = H; q.k = fk; q.pad = (fk - 1) / 2;
         q.y = fy; q.ldy = H;
         launch_tc({q}, 1, fl, fo, maxFrm, B); }
-      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h1, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, pwx.hi, pwx.lo);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), h1, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, pwx.hi, pwx.lo, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       wn_x = wx;
@@ -1219,7 +1248,7 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo, bool pz_rea
   float* wav = ensure(d_wav, (size_t)F * hop + 16);
   const int M = maxFrm * rm * c.istft_hop;
   dim3 g((M + TL_M - 1) / TL_M, B);
-  const size_t smem = ((size_t)(TL_M / 4 + 16) * pc + (size_t)c.subbands * (TL_M + 2 * (62 / 2 / c.subbands + 1))) * sizeof(float);
+  const size_t smem = ((size_t)tl_rec_frames(63, c.subbands, c.istft_n_fft, c.istft_hop) * pc + (size_t)c.subbands * (TL_M + 2 * tl_halo(63, c.subbands))) * sizeof(float);
   REQUIRE(c.istft_hop == 4 && c.istft_n_fft == 16, VTTS_ERR_INVALID, "iSTFT tail kernel is sized for n_fft=16, hop=4");
   klaunch(istft_pqmf_kernel, dim3(g), dim3(TL_THREADS), (size_t)(smem), post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
   CK(cudaGetLastError());
@@ -1334,7 +1363,7 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
   launch_attn(qkv, ao, L, Hc, lens, offs, maxLen, nullptr);
   launch_conv({mk(L.o, ao, Hc, 0, y, Hc, 0, 1, 0)}, 1, lens, offs, maxLen, nB);
   dim3 lg((maxLen + 3) / 4, nB);
-  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), x, y, L.ln1.g, L.ln1.b, nullptr, nullptr, 0, xb, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
+  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), x, y, L.ln1.g, L.ln1.b, nullptr, nullptr, 0, xb, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
   CK(cudaGetLastError());
   ++launches;
   {
@@ -1343,7 +1372,7 @@ void vtts_engine::encoder_layer(const EncLayerW& L, float*& x, float*& xb, float
     launch_conv({p}, 1, lens, offs, maxLen, nB);
   }
   launch_conv({mk(L.ffn2, ffh, Fc, 0, y, Hc, 0, 1, (ks - 1) / 2)}, 1, lens, offs, maxLen, nB);
-  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb, y, L.ln2.g, L.ln2.b, cadd_after, vec_after, vec_ld, x, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
+  klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb, y, L.ln2.g, L.ln2.b, cadd_after, vec_after, vec_ld, x, lens, offs, Hc, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
   CK(cudaGetLastError());
   ++launches;
 }
@@ -1437,15 +1466,15 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   Planes px, px1, pao, pff, pqkv;
   if (enc_on_tc) {
     begin_planes();
-    px = planes(60, (long)T, 1, H); px1 = planes(61, (long)T, 1, H);
-    pao = planes(62, (long)T, 1, H); pff = planes(63, (long)T, 1, Fc);
+    px = planes(60, (long)T, 1, H, 0, enc_three); px1 = planes(61, (long)T, 1, H, 0, enc_three);
+    pao = planes(62, (long)T, 1, H, 0, enc_three); pff = planes(63, (long)T, 1, Fc, 0, enc_three);
     pqkv = planes(59, (long)T, 1, 3 * H);
     flush_tails(tl, to);
   }
   {
     dim3 g(maxTok, B);
     klaunch(embed_kernel, dim3(g), dim3(64), (size_t)(0), ids, enc_emb, x, tl, to, H, sqrtf((float)H), c.n_vocab,
-            (spk_vec && c.cond_layer_idx == 0) ? spk_vec : (const float*)nullptr, condR, px.hi, px.lo);
+            (spk_vec && c.cond_layer_idx == 0) ? spk_vec : (const float*)nullptr, condR, px.hi, px.lo, px.mid);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -1470,7 +1499,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     }
     { TcSpec q; q.in = pao; q.w = L.t_o; q.bias = L.o.b; q.Cin = H; q.Cout = H; q.y = y; q.ldy = H;
       launch_tc({q}, 1, tl, to, maxTok, B); }
-    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, x, y, L.ln1.g, L.ln1.b, (const float*)nullptr, (const float*)nullptr, 0, xb, tl, to, H, px1.hi, px1.lo);
+    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, x, y, L.ln1.g, L.ln1.b, (const float*)nullptr, (const float*)nullptr, 0, xb, tl, to, H, px1.hi, px1.lo, px1.mid);
     ++launches;
     { TcSpec q; q.in = px1; q.w = L.t_ffn1; q.bias = L.ffn1.b; q.Cin = H; q.Cout = Fc; q.k = ks; q.pad = (ks - 1) / 2;
       q.epi = TCE_RELU; q.out = pff; q.pl_slope = 1.f;
@@ -1478,7 +1507,7 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
     { TcSpec q; q.in = pff; q.w = L.t_ffn2; q.bias = L.ffn2.b; q.Cin = Fc; q.Cout = H; q.k = ks; q.pad = (ks - 1) / 2;
       q.y = y; q.ldy = H;
       launch_tc({q}, 1, tl, to, maxTok, B); }
-    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, xb, y, L.ln2.g, L.ln2.b, (const float*)nullptr, va, condR, x, tl, to, H, px.hi, px.lo);
+    klaunch(add_ln_kernel, lg, dim3(128), (size_t)0, xb, y, L.ln2.g, L.ln2.b, (const float*)nullptr, va, condR, x, tl, to, H, px.hi, px.lo, px.mid);
     ++launches;
   }
   // (the prior projection enc_p.proj, models.py:323, is only needed by phase 2: it is enqueued at the end of this phase so
@@ -1533,8 +1562,9 @@ void vtts_engine::phase1(const int* ids_packed_host, const int64_t* d_ids64, int
   int* fl = ensure(d_frm_len, B);
   int* fo = ensure(d_frm_off, B + 1);
   unsigned int* dctr = reinterpret_cast<unsigned int*>(ensure(d_done_ctr, 4));
+  int* fl_real = ensure(d_frm_len_real, B);
   klaunch(duration_kernel, dim3(B), dim3(256), (size_t)(0), zlast, dp_ea, 0, 2, prm, wceil, cum, fl, tl, to, fo, B,
-          (volatile int*)(use_poll ? d_map : nullptr), dctr);
+          (volatile int*)(use_poll ? d_map : nullptr), dctr, fl_real);
   CK(cudaGetLastError());
   ++launches;
   if (!capturing) CK(cudaEventRecord(ev[3], stream));
@@ -1597,7 +1627,7 @@ void vtts_engine::stage1(const int* ids_packed_host, const int* sid_host, int t_
   } else {
     pp.prm[6] = 0.f;
   }
-  pp.prm[7] = 0.f;
+  memcpy(&pp.prm[7], &spec_cap, 4);        // frames the speculative second phase is sized for (0: none), see duration_kernel
   if (noise_dp_host) {        // [B][2][t_max] -> [B][2][maxTok]: the device layout depends on the length bucket only
     for (int r = 0; r < 2 * B; ++r)
       memcpy(pp.eps + (size_t)r * maxTok, noise_dp_host + (size_t)r * t_max, (size_t)std::min(t_max, maxTok) * sizeof(float));
@@ -1704,7 +1734,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
       launch_attn(fqkv, fao, W.tr, H, fl, fo, maxFrm, nullptr);
       launch_conv({mk(W.tr.o, fao, H, 0, fy, H, 0, 1, 0)}, 1, fl, fo, maxFrm, B);
       dim3 lg((maxFrm + 3) / 4, B);
-      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xa, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, xb2, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xa, fy, W.tr.ln1.g, W.tr.ln1.b, nullptr, nullptr, 0, xb2, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       {
@@ -1713,7 +1743,7 @@ void vtts_engine::phase2(const float* noise_z, int z_ld, bool noise_on_device, b
         launch_conv({p}, 1, fl, fo, maxFrm, B);
       }
       launch_conv({mk(W.tr.ffn2, ffh2, H, 0, fy, H, 0, 1, (fk - 1) / 2)}, 1, fl, fo, maxFrm, B);
-      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb2, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
+      klaunch(add_ln_kernel, dim3(lg), dim3(128), (size_t)(0), xb2, fy, W.tr.ln2.g, W.tr.ln2.b, h, nullptr, 0, wx, fl, fo, H, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr, (__nv_bfloat16*)nullptr);
       CK(cudaGetLastError());
       ++launches;
       wn_in = wx;
@@ -1853,7 +1883,7 @@ void vtts_engine::decode(float* z, const int* fl, const int* fo, bool planes_rea
     launch_conv({p}, rm, fl, fo, maxFrm, B);
     const int M = maxFrm * rm * c.istft_hop;
     dim3 g((M + TL_M - 1) / TL_M, B);
-    const size_t smem = ((size_t)(TL_M / 4 + 16) * pc + (size_t)c.subbands * (TL_M + 2 * (62 / 2 / c.subbands + 1))) * sizeof(float);
+    const size_t smem = ((size_t)tl_rec_frames(63, c.subbands, c.istft_n_fft, c.istft_hop) * pc + (size_t)c.subbands * (TL_M + 2 * tl_halo(63, c.subbands))) * sizeof(float);
     REQUIRE(c.istft_hop == 4 && c.istft_n_fft == 16, VTTS_ERR_INVALID, "iSTFT tail kernel is sized for n_fft=16, hop=4");
     klaunch(istft_pqmf_kernel, dim3(g), dim3(TL_THREADS), (size_t)(smem), post, pc, istft_basis, pqmf, c.subbands, c.istft_n_fft, c.istft_hop, 63, rm, fl, fo, wav, 0, 1);
     CK(cudaGetLastError());
@@ -1951,11 +1981,13 @@ void setup_lengths(vtts_handle h, const int64_t* lengths, int B, int t_max) {
 
 namespace {
 
+static bool spec_ok(vtts_handle h, int B);
 static void enqueue_phase1_host(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
-                               const float* scales, const float* noise_dp, uint64_t seed) {
+                               const float* scales, const float* noise_dp, uint64_t seed, bool may_speculate) {
   setup_lengths(h, lengths, B, t_max);
   memcpy(h->scales, scales, 3 * sizeof(float));
   h->seed = seed;
+  h->spec_cap = (may_speculate && spec_ok(h, B)) ? vtts_engine::bucket_frm(h->spec_predict()) : 0;
   std::vector<int> packed(h->Ttok), sid32(B);
   for (int b = 0; b < B; ++b) {
     for (int t = 0; t < h->h_tok_len[b]; ++t) {
@@ -1972,7 +2004,7 @@ static void enqueue_phase1_host(vtts_handle h, const int64_t* ids, const int64_t
 
 static void impl_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
                    const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {
-  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed);
+  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, false);
   h->finish1();
   if (B == 1) h->spec_learn();
   for (int b = 0; b < B; ++b) y_lengths[b] = h->h_frm_len[b];
@@ -2012,10 +2044,11 @@ static void impl_synthesize(vtts_handle h, const float* noise_z, int z_ld, float
 }
 
 static void enqueue_phase1_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
-                              const float* scales, const float* d_noise_dp, uint64_t seed) {
+                              const float* scales, const float* d_noise_dp, uint64_t seed, bool may_speculate) {
   setup_lengths(h, lengths_host, B, t_max);
   memcpy(h->scales, scales, 3 * sizeof(float));
   h->seed = seed;
+  h->spec_cap = (may_speculate && spec_ok(h, B)) ? vtts_engine::bucket_frm(h->spec_predict()) : 0;
   h->stage1(nullptr, nullptr, t_max, nullptr);
   h->eps_dp_ld = t_max;      // device noise is read in the caller's [B][2][t_max] layout
   h->run_graphed({0x33, B, h->maxTok, h->Ttok, t_max, (long long)(uintptr_t)d_ids, (long long)(uintptr_t)d_sid, (long long)(uintptr_t)d_noise_dp},
@@ -2024,7 +2057,7 @@ static void enqueue_phase1_dev(vtts_handle h, const int64_t* d_ids, const int64_
 
 static void impl_durations_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
                        const float* scales, const float* d_noise_dp, uint64_t seed, int64_t* y_lengths_host) {
-  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed);
+  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, false);
   h->finish1();
   if (B == 1) h->spec_learn();
   for (int b = 0; b < B; ++b) y_lengths_host[b] = h->h_frm_len[b];
@@ -2040,9 +2073,9 @@ static bool spec_ok(vtts_handle h, int B) {
 static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max, const float* scales,
                        const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed, int64_t* y_lengths, float* wav, int64_t wav_ld,
                        int32_t* frame_token, int idx_ld, int* phase) {
-  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed);
-  if (spec_ok(h, B)) {
-    h->assume_frames(h->spec_predict());
+  enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, true);
+  if (h->spec_cap > 0) {
+    h->assume_frames(h->spec_cap);
     const int cap = h->maxFrm;
     if (noise_z) h->stage_noise_z(noise_z, z_ld);
     h->run_graphed({0x22, h->B, h->maxFrm, h->Tfrm, noise_z ? 1 : 0}, [&] { h->phase2(noise_z, z_ld, false); });
@@ -2072,8 +2105,9 @@ static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths
       h->have_durations = false;
       return;
     }
-    ++h->spec_misses;                    // predicted bucket too small: run the second phase again with the real shape
-    h->set_frame_shape();
+    ++h->spec_misses;                    // predicted bucket too small (the device-side lengths were clamped to it): true
+    h->set_frame_shape();                //   lengths back, second phase again with the real shape
+    h->klaunch(restore_lengths_kernel, dim3(1), dim3(32), (size_t)0, (const int*)h->d_frm_len_real.p, h->d_frm_len.p, h->d_frm_off.p, h->B);
     h->have_durations = true;
   } else {
     h->finish1();
@@ -2088,9 +2122,9 @@ static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths
 static void impl_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* lengths_host, const int64_t* d_sid, int B, int t_max,
                            const float* scales, const float* d_noise_dp, const float* d_noise_z, int z_ld, uint64_t seed,
                            int64_t* y_lengths_host, float* d_wav, int64_t wav_ld, int* phase) {
-  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed);
-  if (spec_ok(h, B)) {
-    h->assume_frames(h->spec_predict());
+  enqueue_phase1_dev(h, d_ids, lengths_host, d_sid, B, t_max, scales, d_noise_dp, seed, true);
+  if (h->spec_cap > 0) {
+    h->assume_frames(h->spec_cap);
     const int cap = h->maxFrm;
     h->run_graphed({0x44, h->B, h->maxFrm, h->Tfrm, z_ld, (long long)(uintptr_t)d_noise_z}, [&] { h->phase2(d_noise_z, z_ld, true); });
     const size_t ncopy = (size_t)std::min<int64_t>((int64_t)cap * h->hop, wav_ld);
@@ -2113,6 +2147,7 @@ static void impl_infer_dev(vtts_handle h, const int64_t* d_ids, const int64_t* l
     }
     ++h->spec_misses;
     h->set_frame_shape();
+    h->klaunch(restore_lengths_kernel, dim3(1), dim3(32), (size_t)0, (const int*)h->d_frm_len_real.p, h->d_frm_len.p, h->d_frm_off.p, h->B);
     h->have_durations = true;
   } else {
     h->finish1();
@@ -2150,17 +2185,17 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
   h->device = device;
   *out = h;   // returned even on failure so that vtts_last_error() is readable; caller destroys it
   return guarded(h, [&] {
-    REQUIRE(cfg->precision >= 0 && cfg->precision <= 2, VTTS_ERR_INVALID, "unknown precision mode");
+    REQUIRE(cfg->precision >= 0 && cfg->precision <= 3, VTTS_ERR_INVALID, "unknown precision mode");
     if (cfg->precision >= 1) {
       void* fn = nullptr;
       cudaDriverEntryPointQueryResult qres;
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::min(tc_smem_bytes<64>(24 * 1024), 227 * 1024)));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes<128>(16 * 1024)));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       for (int wi = 0; wi < 2; ++wi)
         for (int si = 0; si < 3; ++si) {
           const int S = 2 << si;
@@ -2216,6 +2251,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_NO_GRAPHS")) h->use_graphs = atoi(e) == 0;
     if (const char* e = getenv("VTTS_BUCKETS")) h->use_buckets = atoi(e) != 0;
     if (const char* e = getenv("VTTS_SPEC")) h->use_spec = atoi(e) != 0;
+    if (const char* e = getenv("VTTS_SPEC_MARGIN")) h->spec_margin = (float)atof(e);      // (< 1 forces mispredictions: tests)
     if (const char* e = getenv("VTTS_CAPTURE_FIRST")) h->capture_on_first = atoi(e) != 0;   // 0: capture a bucket's graph on its second call          // 0: never enqueue phase 2 before the lengths are known    // 0: size everything by the exact lengths
     if (const char* e = getenv("VTTS_PREFETCH")) h->use_prefetch = atoi(e) != 0;
     h->bind_weights();
@@ -2251,7 +2287,7 @@ void vtts_destroy(vtts_handle h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   auto fr = [](void* p) { if (p) cudaFree(p); };
   fr(h->d_blob);
-  Buf<int>* ib[] = {&h->d_ids, &h->d_tok_len, &h->d_tok_off, &h->d_sid, &h->d_wceil, &h->d_cum, &h->d_frm_len, &h->d_frm_off, &h->d_ftok, &h->d_done_ctr};
+  Buf<int>* ib[] = {&h->d_ids, &h->d_tok_len, &h->d_tok_off, &h->d_sid, &h->d_wceil, &h->d_cum, &h->d_frm_len, &h->d_frm_off, &h->d_ftok, &h->d_done_ctr, &h->d_frm_len_real};
   for (auto* b : ib) fr(b->p);
   Buf<float>* fb[] = {&h->d_condv, &h->d_x, &h->d_xb, &h->d_qkv, &h->d_ao, &h->d_y, &h->d_ffh, &h->d_stats, &h->d_dA, &h->d_dB, &h->d_dx,
                       &h->d_h29, &h->d_za, &h->d_zb, &h->d_eps_dp, &h->d_z, &h->d_h, &h->d_h1, &h->d_wx, &h->d_acts, &h->d_skip, &h->d_fqkv,

@@ -87,6 +87,20 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __ushort_as_bfloat16((unsigned short)(h >> 16));
   lo = __ushort_as_bfloat16((unsigned short)(l >> 16));
 }
+// fp32 -> (hi, mid, lo) bf16 with hi + mid + lo == x EXACTLY up to the last bit of the fp32 significand (3 x 8 = 24 bits):
+// with the six products hh, hm, mh, hl, lh, mm a tensor-core GEMM then multiplies like an fp32 FMA pipe does (the dropped
+// terms ml, lm, ll are below 2^-26 of the product) and differs from it only in the fp32 summation order.  Used where the
+// result feeds ceil() of a duration (text encoder, precision mode 3).
+__device__ __forceinline__ void split_bf16_3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
+  const uint32_t h = (__float_as_uint(x) + 0x8000u) & 0xFFFF0000u;
+  const float r1 = x - __uint_as_float(h);
+  const uint32_t m = (__float_as_uint(r1) + 0x8000u) & 0xFFFF0000u;
+  const float r2 = r1 - __uint_as_float(m);
+  const uint32_t l = __float_as_uint(r2) + 0x8000u;
+  hi = __ushort_as_bfloat16((unsigned short)(h >> 16));
+  mid = __ushort_as_bfloat16((unsigned short)(m >> 16));
+  lo = __ushort_as_bfloat16((unsigned short)(l >> 16));
+}
 // two values at once, packed as bf16 pairs (a in the low half): PRMT does the packing
 __device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const uint32_t ha = (__float_as_uint(a) + 0x8000u) & 0xFFFF0000u, hb = (__float_as_uint(b) + 0x8000u) & 0xFFFF0000u;
@@ -131,6 +145,7 @@ struct ConvP {
   float alpha;
   __nv_bfloat16* p_hi;   // optional split-bf16 planes of the output (same rows, `ldp` channels per row) for a
   __nv_bfloat16* p_lo;   // tensor-core consumer; written as lrelu(out, pl_slope)
+  __nv_bfloat16* p_mid;  // third plane (exact 3-way split) or null
   int ldp;
   float pl_slope;
 };
@@ -453,8 +468,9 @@ conv_kernel(const __grid_constant__ ConvBatch cb, const int* __restrict__ lens, 
           if (oc + e < climit) {
             float u = v[e] + (rrow ? rrow[e] : 0.f);
             u = u > 0.f ? u : u * P.pl_slope;
-            __nv_bfloat16 hb, lb;
-            split_bf16(u, hb, lb);
+            __nv_bfloat16 hb, lb, mb;
+            if (P.p_mid) { split_bf16_3(u, hb, mb, lb); P.p_mid[orow * (long)P.ldp + oc + e] = mb; }
+            else split_bf16(u, hb, lb);
             P.p_hi[orow * (long)P.ldp + oc + e] = hb;
             P.p_lo[orow * (long)P.ldp + oc + e] = lb;
           }
@@ -493,7 +509,7 @@ __global__ void cond_kernel(const float* __restrict__ emb_g, const int* __restri
 __global__ void embed_kernel(const int* __restrict__ ids, const float* __restrict__ emb, float* __restrict__ x,
                              const int* __restrict__ lens, const int* __restrict__ offs, int H, float scale,
                              int n_vocab, const float* __restrict__ vec, int vec_ld, __nv_bfloat16* __restrict__ p_hi,
-                             __nv_bfloat16* __restrict__ p_lo) {
+                             __nv_bfloat16* __restrict__ p_lo, __nv_bfloat16* __restrict__ p_mid) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.y;
@@ -507,8 +523,9 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
     if (vec) v += vec[(long)b * vec_ld + c];
     x[row * H + c] = v;
     if (p_hi) {
-      __nv_bfloat16 hb, lb;
-      split_bf16(v, hb, lb);
+      __nv_bfloat16 hb, lb, mb;
+      if (p_mid) { split_bf16_3(v, hb, mb, lb); p_mid[row * H + c] = mb; }
+      else split_bf16(v, hb, lb);
       p_hi[row * H + c] = hb;
       p_lo[row * H + c] = lb;
     }
@@ -522,7 +539,8 @@ __global__ void embed_kernel(const int* __restrict__ ids, const float* __restric
 __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, const float* __restrict__ gamma,
                               const float* __restrict__ beta, const float* __restrict__ cadd, const float* __restrict__ vec,
                               int vec_ld, float* __restrict__ out, const int* __restrict__ lens, const int* __restrict__ offs, int C,
-                              __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr) {
+                              __nv_bfloat16* __restrict__ p_hi = nullptr, __nv_bfloat16* __restrict__ p_lo = nullptr,
+                              __nv_bfloat16* __restrict__ p_mid = nullptr) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.y;
@@ -558,8 +576,9 @@ __global__ void add_ln_kernel(const float* __restrict__ a, const float* __restri
     if (vec) u += vec[(long)b * vec_ld + c];
     out[row * C + c] = u;
     if (p_hi) {
-      __nv_bfloat16 hb, lb;
-      split_bf16(u, hb, lb);
+      __nv_bfloat16 hb, lb, mb;
+      if (p_mid) { split_bf16_3(u, hb, mb, lb); p_mid[row * C + c] = mb; }
+      else split_bf16(u, hb, lb);
       p_hi[row * C + c] = hb;
       p_lo[row * C + c] = lb;
     }
@@ -586,7 +605,8 @@ template <int DPL, int R>  // dk = 32*DPL
 __global__ void __launch_bounds__(AT_THREADS)
 attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
             const float* __restrict__ relv, int n_heads, int window, const int* __restrict__ lens,
-            const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+            const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+            __nv_bfloat16* __restrict__ p_mid) {
   PDL_LAUNCH();
   PDL_WAIT();
   constexpr int DK = 32 * DPL;
@@ -779,8 +799,9 @@ attn_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int 
         const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
         out[idx] = o;
         if (p_hi) {
-          __nv_bfloat16 hb, lb;
-          split_bf16(o, hb, lb);
+          __nv_bfloat16 hb, lb, mb;
+          if (p_mid) { split_bf16_3(o, hb, mb, lb); p_mid[idx] = mb; }
+          else split_bf16(o, hb, lb);
           p_hi[idx] = hb;
           p_lo[idx] = lb;
         }
@@ -804,7 +825,8 @@ template <int DPL>  // dk = 32*DPL
 __global__ void __launch_bounds__(ATS_THREADS)
 attn_split_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out, int ldo, const float* __restrict__ relk,
                   const float* __restrict__ relv, int n_heads, int window, int max_tiles, const int* __restrict__ lens,
-                  const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo) {
+                  const int* __restrict__ offs, __nv_bfloat16* __restrict__ p_hi, __nv_bfloat16* __restrict__ p_lo,
+                  __nv_bfloat16* __restrict__ p_mid) {
   PDL_LAUNCH();
   constexpr int DK = 32 * DPL;
   constexpr int KS = DK + 4;
@@ -976,8 +998,9 @@ attn_split_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out
       const long idx = (base + qi) * (long)ldo + head * DK + lane + 32 * e;
       out[idx] = v;
       if (p_hi) {
-        __nv_bfloat16 hb, lb;
-        split_bf16(v, hb, lb);
+        __nv_bfloat16 hb, lb, mb;
+        if (p_mid) { split_bf16_3(v, hb, mb, lb); p_mid[idx] = mb; }
+        else split_bf16(v, hb, lb);
         p_hi[idx] = hb;
         p_lo[idx] = lb;
       }
@@ -1288,7 +1311,8 @@ constexpr int SEQ_GAP = 8;
 __global__ void duration_kernel(const float* __restrict__ z, const float* __restrict__ ea, int ea_ch, int ea_n, const float* __restrict__ prm,
                                 int* __restrict__ wceil, int* __restrict__ cum, int* __restrict__ ylen,
                                 const int* __restrict__ lens, const int* __restrict__ offs,
-                                int* __restrict__ yoff, int B, volatile int* host_out, unsigned int* __restrict__ done_counter) {
+                                int* __restrict__ yoff, int B, volatile int* host_out, unsigned int* __restrict__ done_counter,
+                                int* __restrict__ ylen_real) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.x;
@@ -1333,21 +1357,45 @@ __global__ void duration_kernel(const float* __restrict__ z, const float* __rest
     const unsigned int ticket = atomicAdd(done_counter, 1u);
     if (ticket == (unsigned int)B - 1u) {
       __threadfence();
-      int o = 0;
+      // prm[7] > 0: the host has already enqueued the second phase for a PREDICTED length bucket of that many frames
+      // (speculative phase 2).  Its buffers, tensor maps and grids are sized for the bucket, so the device-side lengths it
+      // reads are clamped to it; the host gets the true lengths, sees that the prediction was too small and repeats the
+      // phase after restoring them from ylen_real (restore_lengths_kernel).
+      const int cap = __float_as_int(prm[7]);
+      int o = 0, o_real = 0;
       for (int b2 = 0; b2 < B; ++b2) {
         const int yl = *((volatile int*)&ylen[b2]);
+        ylen_real[b2] = yl;
+        const int ylc = (cap > 0 && yl > cap) ? cap : yl;
+        if (ylc != yl) ylen[b2] = ylc;
         yoff[b2] = o;
-        if (host_out) { host_out[1 + b2] = yl; host_out[1 + B + b2] = o; }
-        o += yl + (b2 + 1 < B ? SEQ_GAP : 0);
+        if (host_out) { host_out[1 + b2] = yl; host_out[1 + B + b2] = o_real; }
+        o += ylc + (b2 + 1 < B ? SEQ_GAP : 0);
+        o_real += yl + (b2 + 1 < B ? SEQ_GAP : 0);
       }
       yoff[B] = o;
       if (host_out) {
-        host_out[1 + 2 * B] = o;
+        host_out[1 + 2 * B] = o_real;
         __threadfence_system();
         host_out[0] = __float_as_int(prm[6]);
       }
       *done_counter = 0u;
     }
+  }
+}
+
+// After a mispredicted speculative second phase: the true frame counts back into the arrays the kernels read.
+__global__ void restore_lengths_kernel(const int* __restrict__ ylen_real, int* __restrict__ ylen, int* __restrict__ yoff, int B) {
+  PDL_LAUNCH();
+  PDL_WAIT();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int o = 0;
+    for (int b = 0; b < B; ++b) {
+      ylen[b] = ylen_real[b];
+      yoff[b] = o;
+      o += ylen_real[b] + (b + 1 < B ? SEQ_GAP : 0);
+    }
+    yoff[B] = o;
   }
 }
 
@@ -1385,7 +1433,7 @@ __global__ void frame_offsets_kernel(const int* __restrict__ ylen, int* __restri
 // out-of-bounds fill.  This replaces per-call memsets of whole planes and lets captured graphs serve any length in a bucket.
 constexpr int ZT_ROWS = 32, ZT_MAXP = 56;
 struct TailList {
-  struct E { __nv_bfloat16* hi; __nv_bfloat16* lo; int C, rm, extra, rows_cap; } e[ZT_MAXP];
+  struct E { __nv_bfloat16* hi; __nv_bfloat16* lo; __nv_bfloat16* mid; int C, rm, extra, rows_cap; } e[ZT_MAXP];
   int n;
 };
 __global__ void zero_tails_kernel(const __grid_constant__ TailList tl, const int* __restrict__ lens, const int* __restrict__ offs, int B) {
@@ -1393,16 +1441,30 @@ __global__ void zero_tails_kernel(const __grid_constant__ TailList tl, const int
   PDL_WAIT();
   const TailList::E& e = tl.e[blockIdx.x];
   const int b = blockIdx.y;
-  const long start = ((long)offs[b] + lens[b]) * e.rm + (long)(b + 1) * e.extra;
-  long stop = start + ZT_ROWS;
-  if (b + 1 < B) stop = min(stop, (long)offs[b + 1] * e.rm + (long)(b + 1) * e.extra);
-  stop = min(stop, (long)e.rows_cap);
-  const long n8 = (stop - start) * e.C / 8;          // C % 8 == 0: rows are 16-byte multiples
-  if (n8 <= 0) return;
-  uint4* ph = reinterpret_cast<uint4*>(e.hi + start * e.C);
-  uint4* pl = reinterpret_cast<uint4*>(e.lo + start * e.C);
+  // rows behind utterance b: [end, end + ZT_ROWS) -- and, when another utterance follows, also the ZT_ROWS rows in front of
+  // ITS first row (its convs' leading halo); a gap of up to 2 * ZT_ROWS rows is simply cleared as a whole
+  const long end = ((long)offs[b] + lens[b]) * e.rm + (long)(b + 1) * e.extra;
+  long a0 = end, a1 = end + ZT_ROWS, b0 = 0, b1 = 0;
+  if (b + 1 < B) {
+    const long next = (long)offs[b + 1] * e.rm + (long)(b + 1) * e.extra;
+    if (next - end <= 2 * ZT_ROWS) a1 = next;
+    else { b0 = next - ZT_ROWS; b1 = next; }
+  }
+  a1 = min(a1, (long)e.rows_cap);
+  b1 = min(b1, (long)e.rows_cap);
   const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-  for (long i = threadIdx.x; i < n8; i += blockDim.x) { ph[i] = z; pl[i] = z; }
+  for (int part = 0; part < 2; ++part) {
+    const long r0 = part ? b0 : a0, r1 = part ? b1 : a1;
+    const long n8 = (r1 - r0) * e.C / 8;           // C % 8 == 0: rows are 16-byte multiples
+    if (n8 <= 0) continue;
+    uint4* ph = reinterpret_cast<uint4*>(e.hi + r0 * e.C);
+    uint4* pl = reinterpret_cast<uint4*>(e.lo + r0 * e.C);
+    for (long i = threadIdx.x; i < n8; i += blockDim.x) { ph[i] = z; pl[i] = z; }
+    if (e.mid) {
+      uint4* pm = reinterpret_cast<uint4*>(e.mid + r0 * e.C);
+      for (long i = threadIdx.x; i < n8; i += blockDim.x) pm[i] = z;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1472,6 +1534,12 @@ __global__ void mrf_mean_kernel(const float* __restrict__ a, const float* __rest
 // ------------------------------------------------------------------------------------------------
 constexpr int TL_M = 64;        // subband samples per CTA (256 output samples): 4x more CTAs than the first version, 40 -> ~12 us at batch 1
 constexpr int TL_THREADS = 256;
+// frames of conv_post output one CTA stages: its TL_M subband samples plus the filter halo on both sides ((taps-1)/2 output
+// samples = (taps-1)/2/subbands + 1 subband samples) plus the n_fft-sample reach of a frame, at `hop` samples per frame
+__host__ __device__ constexpr int tl_halo(int taps, int subbands) { return (taps - 1) / 2 / subbands + 1; }
+__host__ __device__ constexpr int tl_rec_frames(int taps, int subbands, int nfft, int hop) {
+  return (TL_M + 2 * tl_halo(taps, subbands) + nfft) / hop + 2;
+}
 
 __global__ void __launch_bounds__(TL_THREADS)
 istft_pqmf_kernel(const float* __restrict__ post, int ldp, const float* __restrict__ basis, const float* __restrict__ pqmf,
@@ -1498,7 +1566,7 @@ istft_pqmf_kernel(const float* __restrict__ post, int ldp, const float* __restri
   const int nf = f_hi - f_lo + 1;
   extern __shared__ float sm[];
   float* rec = sm;                                   // [nf][subbands*cps]  (re[0..nbins) | im[0..nbins)) per subband
-  float* ysub = rec + (size_t)(TL_M / 4 + 16) * subbands * cps;   // [subbands][TL_M + 2*halo]
+  float* ysub = rec + (size_t)tl_rec_frames(taps, subbands, nfft, hop) * subbands * cps;   // [subbands][TL_M + 2*halo]
   const int yw = TL_M + 2 * halo;
   const long prow0 = (long)frm_off[b] * up_total + b;
   for (int i = threadIdx.x; i < nf * subbands * nbins; i += TL_THREADS) {

@@ -130,11 +130,9 @@ def make_c_config(cfg, precision=0):
     c.spk_cond_encoder = int(bool(cfg["use_spk_conditioned_encoder"]) and cfg["gin_channels"] > 0 and cfg["n_speakers"] > 0)
     c.use_transformer_flows = int(bool(cfg["use_transformer_flows"]))
     c.dp_tail_bound = float(cfg["dp_tail_bound"])
-    if cfg["decoder"] in ("ms_istft", "istft"):
-        # oracle + packing exist and are pinned against the reference on CPU (tests/test_decoder_variants.py); the CUDA tail
-        # kernel has only been exercised with the 4-band PQMF bank, so these stay closed until a GPU parity run has covered them
-        raise NotImplementedError("decoder %r: packed and pinned on CPU, not yet validated on the GPU" % cfg["decoder"])
-    c.decoder_type = 0 if cfg["decoder"] == "mb_istft" else 1
+    # 0: conv_post -> exp / pi*sin -> inverse STFT -> 63-tap filter bank (Multiband_ / Multistream_ / plain iSTFT_Generator differ only
+    #    in the bank: fixed PQMF, learned, unit impulse; models.py:901-971, 974-1063, 1066-1169); 1: HiFi-GAN Generator
+    c.decoder_type = 0 if cfg["decoder"] in ("mb_istft", "ms_istft", "istft") else 1
     c.resblock_type = 1 if str(cfg["resblock"]) == "1" else 2
     rk, rd = cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"]
     c.n_resblock_kernels = len(rk)

@@ -143,6 +143,22 @@ class _Packer:
         self.add(name + ".th", hi.reshape(-1).view(np.float32))
         self.add(name + ".tl", lo.reshape(-1).view(np.float32))
 
+    def conv_tc3(self, name, w, co_perm=None, ci_perm=None):
+        """Exact 3-way split copy (precision mode 3): <name>.t3h / .t3m / .t3l with hi + mid + lo == w to the last fp32 bit."""
+        w = np.asarray(w, np.float32)
+        if co_perm is not None:
+            w = w[co_perm]
+        if ci_perm is not None:
+            w = w[:, ci_perm]
+        wt = np.ascontiguousarray(np.transpose(w, (2, 0, 1)))          # [k][Cout][Cin]
+        hi = to_bf16_bits(wt)
+        r1 = wt - from_bf16_bits(hi)
+        mid = to_bf16_bits(r1)
+        lo = to_bf16_bits(r1 - from_bf16_bits(mid))
+        self.add(name + ".t3h", hi.reshape(-1).view(np.float32))
+        self.add(name + ".t3m", mid.reshape(-1).view(np.float32))
+        self.add(name + ".t3l", lo.reshape(-1).view(np.float32))
+
     def finish(self):
         blob = np.concatenate(self.chunks) if self.chunks else np.zeros(0, np.float32)
         manifest = "".join("%s %d %d\n" % e for e in self.entries)
@@ -180,8 +196,9 @@ def pack(w, cfg, tc=True, precision=None):
     one-time NCCL weight broadcast of a multi-GPU job."""
     tc = tc and tc_supported(cfg) and precision != 0
     enc_tc = tc and precision in (None, 2)
-    fw = not (tc and precision in (1, 2))      # fp32 copies of the flow / decoder convs (the tcgen05 modes read only .th/.tl + bias)
-    ew = not (tc and precision == 2)           # ... of the text encoder's convs
+    enc_tc3 = tc and precision in (None, 3)    # exact 3-way split copies of the text encoder's convs (mode 3)
+    fw = not (tc and precision in (1, 2, 3))   # fp32 copies of the flow / decoder convs (the tcgen05 modes read only .th/.tl + bias)
+    ew = not (tc and precision in (2, 3))      # ... of the text encoder's convs
     g = lambda k: w[k].detach().cpu().numpy() if hasattr(w[k], "detach") else np.asarray(w[k])
     H, I, G = cfg["hidden_channels"], cfg["inter_channels"], cfg["gin_channels"]
     D = cfg["dp_filter_channels"]
@@ -191,7 +208,7 @@ def pack(w, cfg, tc=True, precision=None):
         P.add(dst + ".g", g(src + ".gamma"))
         P.add(dst + ".b", g(src + ".beta"))
 
-    def enc_layer(dst, src, i, with_tc=False, need_w=True):
+    def enc_layer(dst, src, i, with_tc=False, need_w=True, with_tc3=False):
         a = "%s.attn_layers.%d" % (src, i)
         wq = np.concatenate([g(a + ".conv_q.weight"), g(a + ".conv_k.weight"), g(a + ".conv_v.weight")], 0)
         bq = np.concatenate([g(a + ".conv_q.bias"), g(a + ".conv_k.bias"), g(a + ".conv_v.bias")], 0)
@@ -203,6 +220,12 @@ def pack(w, cfg, tc=True, precision=None):
             P.conv_tc(dst + ".o", g(a + ".conv_o.weight"))
             P.conv_tc(dst + ".ffn1", g(f_ + ".conv_1.weight"))
             P.conv_tc(dst + ".ffn2", g(f_ + ".conv_2.weight"))
+        if with_tc3:
+            f_ = "%s.ffn_layers.%d" % (src, i)
+            P.conv_tc3(dst + ".qkv", wq)
+            P.conv_tc3(dst + ".o", g(a + ".conv_o.weight"))
+            P.conv_tc3(dst + ".ffn1", g(f_ + ".conv_1.weight"))
+            P.conv_tc3(dst + ".ffn2", g(f_ + ".conv_2.weight"))
         P.add(dst + ".relk", g(a + ".emb_rel_k")[0])
         P.add(dst + ".relv", g(a + ".emb_rel_v")[0])
         if with_tc:
@@ -258,10 +281,12 @@ def pack(w, cfg, tc=True, precision=None):
     # ---- text encoder
     P.add("enc.emb", g("enc_p.emb.weight"))
     for i in range(cfg["n_layers"]):
-        enc_layer("enc.%d" % i, "enc_p.encoder", i, with_tc=enc_tc, need_w=ew)
+        enc_layer("enc.%d" % i, "enc_p.encoder", i, with_tc=enc_tc, need_w=ew, with_tc3=enc_tc3)
     P.conv("enc.proj", g("enc_p.proj.weight"), g("enc_p.proj.bias"), need_w=ew)
     if enc_tc:
         P.conv_tc("enc.proj", g("enc_p.proj.weight"))
+    if enc_tc3:
+        P.conv_tc3("enc.proj", g("enc_p.proj.weight"))
 
     # ---- stochastic duration predictor
     P.conv("dp.pre", g("dp.pre.weight"), g("dp.pre.bias"))
