@@ -40,3 +40,50 @@ print("C  distinct utterances, T = 128     :", timed(lambda: sess.run(None, feed
 print("D  distinct utterances, T = 100..128:", timed(lambda: sess.run(None, feeds(int(torch.randint(100, 129, (1,), generator=g)))), 30, 60))
 print("   speculation", eng.speculation_stats(), "replays", eng.graph_replays())
 os.environ["X"] = "1"
+
+# ---- GPU-side span (first to last kernel entry stamp, %globaltimer) next to the wall time of the same call
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+def span(fn, label, do_flush):
+    res = []
+    for _ in range(8):
+        if do_flush:
+            flush.fill_(1)
+        torch.cuda.synchronize()
+        eng.timeline(1)
+        t = time.perf_counter(); fn(); wall = (time.perf_counter() - t) * 1e3
+        tl = eng.timeline(2); eng.timeline(0)
+        ts = np.sort(tl[:, 1].astype(np.int64))
+        gaps = np.diff(ts)
+        res.append((wall, (ts[-1] - ts[0]) / 1e6, len(ts), gaps.max() / 1e3, int(np.argmax(gaps))))
+    res.sort()
+    w, s_, n, g_, gi = res[len(res) // 2]
+    print("%-44s wall %.3f ms  gpu span %.3f ms  stamps %d  largest gap %.1f us at stamp %d" % (label, w, s_, n, g_, gi))
+span(lambda: sess.run(None, fA, noise=nz), "A same utterance, caller noise", False)
+span(lambda: sess.run(None, fA), "B same utterance, engine noise", False)
+span(lambda: sess.run(None, feeds(128)), "C distinct utterances", False)
+span(lambda: sess.run(None, fA, noise=nz), "A + L2 flush", True)
+span(lambda: sess.run(None, fA), "B + L2 flush", True)
+span(lambda: sess.run(None, feeds(128)), "C + L2 flush", True)
+
+# ---- does switching between captured graphs cost anything?  Two FIXED utterances (caller noise => fixed durations)
+def fixed(T, seed):
+    gg = torch.Generator().manual_seed(seed)
+    f = {"input": torch.randint(0, 62, (1, T), generator=gg).numpy().astype(np.int64), "input_lengths": np.array([T], np.int64),
+         "scales": scales, "sid": np.array([2], np.int64), "bert": None, "phone_duration_extra": None}
+    nd = {"dp": torch.randn(1, 2, T, generator=gg).numpy(), "z": torch.randn(1, 192, 600, generator=gg).numpy()}
+    sess.run(None, f, noise=nd)
+    ty = int(sess.last_y_lengths[0])
+    return f, {"dp": nd["dp"], "z": np.ascontiguousarray(nd["z"][:, :, :ty])}, ty
+u1, n1, t1 = fixed(128, 11)
+u2, n2, t2 = fixed(128, 12)
+u3, n3, t3 = fixed(100, 13)
+print("frames of the three fixed utterances:", t1, t2, t3)
+state = {"i": 0}
+def alt(pairs):
+    def f():
+        u, n = pairs[state["i"] % len(pairs)]; state["i"] += 1
+        sess.run(None, u, noise=n)
+    return f
+print("E1 one fixed utterance                     :", timed(alt([(u1, n1)]), 30, 6))
+print("E2 two fixed utterances alternating (T=128):", timed(alt([(u1, n1), (u2, n2)]), 30, 6))
+print("E3 two fixed utterances alternating (128/100):", timed(alt([(u1, n1), (u3, n3)]), 30, 6))

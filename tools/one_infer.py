@@ -11,8 +11,9 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     cfg = C.DEFAULT_CONFIG
     wl = bench.workload(cfg)
-    blob, man = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg)
-    eng = Engine(cfg, blob, man, device=0, precision=int(os.environ.get('PRECISION', '0')))
+    prec = int(os.environ.get('PRECISION', '1'))
+    blob, man = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg, precision=prec)
+    eng = Engine(cfg, blob, man, device=0, precision=prec)
     eng.set_graphs(False)
     for i in range(n):
         t0 = time.perf_counter()

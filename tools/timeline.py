@@ -9,7 +9,7 @@ import bench
 
 def kernel_names():
     names = {}
-    for fn in ("kernels.cuh", "conv_tc.cuh", "attn_tc.cuh"):
+    for fn in ("kernels.cuh", "conv_tc.cuh", "attn_tc.cuh", "wn_tc.cuh"):
         cur = None
         for i, line in enumerate(open(os.path.join(ROOT, "vosk_tts_b200", "csrc", fn)), 1):
             m = re.search(r"^(?:__global__.*?\s|)(\w+_kernel)\s*\(", line)

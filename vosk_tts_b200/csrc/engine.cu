@@ -25,6 +25,7 @@
 #include "kernels.cuh"
 #include "conv_tc.cuh"
 #include "attn_tc.cuh"
+#include "wn_tc.cuh"
 
 using namespace vtts;
 
@@ -301,6 +302,7 @@ struct vtts_engine {
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
   cudaEvent_t ev_fork = nullptr, ev_join[3] = {};
   int attn_tc_mode = 1;                    // tcgen05 attention where the qkv conv runs on tensor cores: 0 never, 1 when throughput bound, 2 always
+  int mrf_heavy_first = 1;
   int mrf_branch = 0;                      // VTTS_MRF_BRANCH=1: one stream per resblock chain (measured slower: 1.74 vs 1.62 ms)
   float stage_ms[8] = {};
   bool ev_valid = false;
@@ -517,7 +519,19 @@ struct vtts_engine {
   void launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* lens, const int* offs, int maxLen, int nB);
   // plane buffers of the frame-resolution stages: allocated (and their tails zeroed by ONE zero_tails launch) before the
   // first kernel of the phase
-  struct FlowPl { Planes ph, pao, ph1, pff, pwx, pacts, pskip, pqkv; } flp;
+  struct FlowPl { Planes ph, pao, ph1, pff, pwx, pwx2, pacts, pskip, pqkv; } flp;
+  // One cluster kernel per WN layer (wn_tc.cuh).  Correct (all goldens), but measured SLOWER than the two launches it
+  // replaces: 36 vs 22 us per layer at batch 1 (1.94 vs 1.69 ms per utterance) -- without split-K the 15 k-steps of the gated
+  // conv run serially in each CTA (8.7 us), the gate for 48 channels per thread costs 4.3 us, the DSMEM all-gather of the
+  // 96 KB acts tile 4.1 us plus two cluster barriers, and the second epilogue 10.8 us (profiles/r2_timeline_wn_fused_nopdl.txt).
+  // Kept behind VTTS_WN_FUSED=1.
+  int wn_fused = 0;
+  bool wn_fused_ok() const {
+    const int H = cfg.hidden_channels;
+    return wn_fused && (H == 64 || H == 128 || H == 192) && cfg.flow_kernel_size % 2 == 1;
+  }
+  void launch_wn_fused(const FlowW& W, int f, int i, const Planes& xin, const Planes& xout, float* x, float* skip, const Planes& pskip,
+                       int dil, const int* fl, const int* fo);
   struct DecPl { Planes pz, cur; std::vector<Planes> px, nxt; std::vector<std::vector<Planes>> pj, pt; } dcp;
   void alloc_flow_planes();
   void alloc_decoder_planes();
@@ -1021,6 +1035,66 @@ void vtts_engine::alloc_flow_planes() {
   flp.pff = planes(slot++, F, 1, H); flp.pwx = planes(slot++, F, 1, H); flp.pacts = planes(slot++, F, 1, H);
   flp.pskip = planes(slot++, F, 1, H);
   flp.pqkv = planes(slot++, F, 1, 3 * H);
+  flp.pwx2 = planes(slot++, F, 1, H);
+}
+
+// One WaveNet layer as a single cluster kernel (wn_tc.cuh): reads the planes `xin`, writes the updated hidden state to
+// x (fp32, in place) and to the OTHER plane set `xout` (neighbouring row tiles still read `xin` for their conv halos).
+void vtts_engine::launch_wn_fused(const FlowW& W, int f, int i, const Planes& xin, const Planes& xout, float* x, float* skip,
+                                  const Planes& pskip, int dil, const int* fl, const int* fo) {
+  const vtts_config& c = cfg;
+  const int H = c.hidden_channels, nl = c.flow_wn_layers, fk = c.flow_kernel_size;
+  const bool last = (i == nl - 1);
+  const int BN1 = 2 * H / WN_NCL, BN2 = (last ? H : 2 * H) / WN_NCL;
+  WnParams wp;
+  memset(&wp, 0, sizeof(wp));
+  wp.a_hi = make_map(xin.hi, H, xin.rows, 128);
+  wp.a_lo = make_map(xin.lo, H, xin.rows, 128);
+  wp.win_hi = make_map(W.t_in[i].hi, H, (long)fk * 2 * H, BN1);
+  wp.win_lo = make_map(W.t_in[i].lo, H, (long)fk * 2 * H, BN1);
+  if (!last) {
+    wp.wrx_hi = make_map(W.t_rsx[i].hi, H, H, BN2);
+    wp.wrx_lo = make_map(W.t_rsx[i].lo, H, H, BN2);
+    wp.bias_rx = W.rsx[i].b;
+  }
+  wp.wrs_hi = make_map(W.t_rss[i].hi, H, H, BN2);
+  wp.wrs_lo = make_map(W.t_rss[i].lo, H, H, BN2);
+  wp.bias_rs = W.rss[i].b;
+  wp.bias_in = W.in[i].b;
+  if (has_g) { wp.cond = d_condv.p + r_flow + (f * nl + i) * 2 * H; wp.cond_ld = condR; }
+  wp.x = x; wp.xp_hi = xout.hi; wp.xp_lo = xout.lo;
+  wp.skip = skip;
+  if (last) { wp.sp_hi = pskip.hi; wp.sp_lo = pskip.lo; }
+  wp.k = fk; wp.dil = dil; wp.pad = dil * (fk - 1) / 2;
+  wp.first = (i == 0) ? 1 : 0;
+  dim3 grid((maxFrm + 127) / 128, WN_NCL, B);
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = grid; lc.blockDim = dim3(WN_THREADS); lc.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeClusterDimension;
+  at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = WN_NCL; at[na].val.clusterDim.z = 1;
+  ++na;
+  if (use_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  lc.attrs = at; lc.numAttrs = na;
+#define WN_LAUNCH(HH)                                                                                                   \
+  do {                                                                                                                  \
+    lc.dynamicSmemBytes = wn_smem_bytes<HH>();                                                                          \
+    if (last) CK(cudaLaunchKernelEx(&lc, wn_layer_tc_kernel<HH, true>, wp, fl, fo));                                    \
+    else CK(cudaLaunchKernelEx(&lc, wn_layer_tc_kernel<HH, false>, wp, fl, fo));                                        \
+  } while (0)
+  if (H == 192) WN_LAUNCH(192); else if (H == 128) WN_LAUNCH(128); else WN_LAUNCH(64);
+#undef WN_LAUNCH
+  CK(cudaGetLastError());
+  if (profiling) {   // counted with the tcgen05 conv family (algorithmic FLOPs of both GEMMs)
+    for (int b = 0; b < B; ++b) tc_prof_flops += 2.0 * h_frm_len[b] * ((double)2 * H * H * fk + (double)(last ? H : 2 * H) * H);
+  }
+  ++launches;
 }
 void vtts_engine::alloc_decoder_planes() {
   const vtts_config& c = cfg;
@@ -1056,6 +1130,7 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo, bool emit_pz) 
   float* fqkv = ensure(d_fqkv, (size_t)F * 3 * H);
   float* fao = ensure(d_fao, (size_t)F * H);
   Planes ph = flp.ph, pao = flp.pao, ph1 = flp.ph1, pff = flp.pff, pwx = flp.pwx, pacts = flp.pacts, pskip = flp.pskip, pqkv = flp.pqkv;
+  const bool fused = wn_fused_ok();
   dim3 lg((maxFrm + 3) / 4, B);
   for (int f = nf - 1; f >= 0; --f) {
     const FlowW& W = flow[f];
@@ -1096,7 +1171,12 @@ void vtts_engine::flow_tc(float* z, const int* fl, const int* fo, bool emit_pz) 
       wn_x = wx;
     }
     int dil = 1;
-    for (int i = 0; i < nl; ++i) {
+    for (int i = 0; i < nl && fused; ++i) {
+      // layer i reads the hidden state's planes from one buffer and writes the updated ones to the other
+      launch_wn_fused(W, f, i, (i % 2 == 0) ? pwx : flp.pwx2, (i % 2 == 0) ? flp.pwx2 : pwx, wn_x, skip, pskip, dil, fl, fo);
+      dil *= c.flow_dilation_rate;
+    }
+    for (int i = 0; i < nl && !fused; ++i) {
       { TcSpec q; q.in = pwx; q.w = W.t_in[i]; q.bias = W.in[i].b; q.Cin = H; q.Cout = 2 * H; q.k = fk; q.dil = dil;
         q.pad = dil * (fk - 1) / 2; q.epi = TCE_GATE; q.out = pacts; q.pl_slope = 1.f;
         if (has_g) { q.cond = d_condv.p + r_flow + (f * nl + i) * 2 * H; q.cond_ld = condR; }
@@ -1218,7 +1298,9 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo, bool pz_rea
     } else {
       for (int d = 0; d < nd; ++d) {
         std::vector<TcSpec> p1(nk), p2(nk);
-        for (int j = 0; j < nk; ++j) rb_pair(j, d, p1[j], p2[j]);
+        // CTAs are dispatched in blockIdx.z order = problem order: the resblock with the longest k-loop (largest kernel
+        // size) goes first, so that a second wave holds the short ones
+        for (int j = 0; j < nk; ++j) rb_pair(j, d, p1[mrf_heavy_first ? nk - 1 - j : j], p2[mrf_heavy_first ? nk - 1 - j : j]);
         launch_tc(p1, rm, fl, fo, maxFrm, B);
         launch_tc(p2, rm, fl, fo, maxFrm, B);
       }
@@ -2241,6 +2323,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
     if (const char* e = getenv("VTTS_MRF_BRANCH")) h->mrf_branch = atoi(e);
+    if (const char* e = getenv("VTTS_MRF_HEAVY_FIRST")) h->mrf_heavy_first = atoi(e);
+    if (const char* e = getenv("VTTS_WN_FUSED")) h->wn_fused = atoi(e);
     if (const char* e = getenv("VTTS_ATTN_SPLIT")) h->attn_split = atoi(e);       // 0: never use the split-KV attention
     if (const char* e = getenv("VTTS_CONV_AUTOG")) h->conv_auto_g = std::max(0, atoi(e));   // k-steps per rank needed to add thread groups; 0 = never
     if (const char* e = getenv("VTTS_CONV_MING")) h->conv_min_g = std::max(1, std::min(4, atoi(e)));      // 0 auto, 1 off, 2/4/8 cap
@@ -2258,6 +2342,12 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->build_prefetch_list();
     CK(cudaMemsetAsync(h->ensure(h->d_done_ctr, 4), 0, 4 * sizeof(int), h->stream));     // ticket counter of duration_kernel (self-resetting)
     CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<128>()));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<128>()));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<64>()));
+    CK(cudaFuncSetAttribute(wn_layer_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<64>()));
     CK(cudaFuncSetAttribute(attn_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(32)));
     CK(cudaFuncSetAttribute(attn_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(64)));
     CK(cudaFuncSetAttribute(attn_tc_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, atc_smem_bytes(96)));
