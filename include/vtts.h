@@ -145,6 +145,9 @@ uint64_t vtts_graph_replays(vtts_handle h);
  * for the durations (the kernels read the true lengths on the device) and repeat it only when the prediction was too small:
  * hits / misses since creation. */
 int vtts_speculation_stats(vtts_handle h, uint64_t* hits, uint64_t* misses);
+/* Host-side wall clock (microseconds) of the last single-utterance vtts_infer call: [0] phase-1 enqueue, [1] phase-2 +
+ * copy-back enqueue, [2] wait for the stream, [3] copy-out, [4] total, [5] 1 = speculative hit, 2 = miss, 0 = not speculative. */
+int vtts_host_timings(vtts_handle h, double* us, int n);
 
 /* Per-launch profiling of the dense-conv kernel family (the dominant kernels): while enabled every launch is
  * bracketed by CUDA events on the engine's stream.  vtts_profile_read returns the summed device time, the

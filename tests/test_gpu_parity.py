@@ -323,17 +323,19 @@ def test_speculative_second_phase_hits_and_misses(packed, cfg, margin):
     whose frame count does not fit the under-sized bucket takes the repeat path."""
     import os
     from vosk_tts_b200.engine import Engine
-    old = os.environ.get("VTTS_SPEC_MARGIN")
+    env = {"VTTS_SPEC": "1"}                       # (speculation is opt-in: see vtts_engine::use_spec)
     if margin is not None:
-        os.environ["VTTS_SPEC_MARGIN"] = margin
+        env["VTTS_SPEC_MARGIN"] = margin
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
     try:
         engine = Engine(cfg, packed[0], packed[1], device=0, precision=1)
     finally:
-        if margin is not None:
-            if old is None:
-                os.environ.pop("VTTS_SPEC_MARGIN", None)
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
             else:
-                os.environ["VTTS_SPEC_MARGIN"] = old
+                os.environ[k] = v
     g = torch.Generator().manual_seed(91)
     plan = [(100, 1.0), (90, 1.0), (110, 1.1), (100, 0.25), (96, 1.0), (100, 2.0), (64, 1.0), (128, 1.0), (128, 1.0)]
     for T, ls in plan:

@@ -198,12 +198,19 @@ struct vtts_engine {
   // behind phase 1 WITHOUT the host waiting for the lengths, and repeated with the right bucket in the rare case the
   // prediction was too small.  A whole utterance is then two graph launches and one synchronisation; the phase-1 ->
   // host -> phase-2 round trip (~50 us, and the part of a step most exposed to host jitter) is gone.
-  bool use_spec = true;
+  // OFF by default (VTTS_SPEC=1): measured on never-seen utterances with random speakers, whose frames-per-token ratio is
+  // heavy tailed (1.3 .. 4), the predicted bucket is usually far too large (the predictor must cover the recent maximum or pay a
+  // repeat), the launch heuristics then size split-K / tiles / attention for 3x the rows, and the GPU part of a call grows
+  // from 1.7 to 2.5 ms -- while the round trip it removes was already hidden behind the prior projection (value: 1.665 vs
+  // 1.666 ms with and without).  It only pays for repeated or very regular texts.
+  bool use_spec = false;
   float spec_hist[16] = {};
   int spec_n = 0;
   float spec_ratio = 0.f;
   uint64_t spec_hits = 0, spec_misses = 0;
   double spec_units() const { return (double)real_maxTok * (double)std::max(0.05f, scales[1]); }
+  double host_us[8] = {};             // host-side wall clock of the last vtts_infer call: [0] phase-1 enqueue, [1] phase-2 enqueue
+                                      //   (+ copy-back enqueue), [2] wait for the stream, [3] copy-out, [4] total, [5] 1 = speculative hit, 2 = miss
   int spec_cap = 0;                   // length bucket of the speculative second phase of the current call (0: not speculating)
   float spec_margin = 1.08f;
   int spec_predict() const { return (int)std::ceil((double)spec_ratio * spec_margin * spec_units()) + 8; }
@@ -226,7 +233,9 @@ struct vtts_engine {
   }
   int eps_dp_ld = 0;                 // row pitch of the duration-predictor noise the phase-1 kernels read
   static int bucket_tok(int n) { return n <= 256 ? (n + 15) / 16 * 16 : (n + 63) / 64 * 64; }
-  static int bucket_frm(int n) { return n <= 512 ? (n + 31) / 32 * 32 : (n <= 4096 ? (n + 127) / 128 * 128 : (n + 511) / 512 * 512); }
+  static int bucket_frm(int n) {
+    return n <= 256 ? (n + 31) / 32 * 32 : (n <= 1024 ? (n + 63) / 64 * 64 : (n <= 4096 ? (n + 127) / 128 * 128 : (n + 511) / 512 * 512));
+  }
   static void virtual_lens(std::vector<int>& v, int nB, int total_cap, int max_cap) {
     const int per = std::max(1, std::min(max_cap, (total_cap - (nB - 1) * SEQ_GAP + nB - 1) / nB));
     v.assign(nB, per);
@@ -2155,7 +2164,12 @@ static bool spec_ok(vtts_handle h, int B) {
 static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max, const float* scales,
                        const float* noise_dp, const float* noise_z, int z_ld, uint64_t seed, int64_t* y_lengths, float* wav, int64_t wav_ld,
                        int32_t* frame_token, int idx_ld, int* phase) {
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_0 = now_us();
   enqueue_phase1_host(h, ids, lengths, sid, B, t_max, scales, noise_dp, seed, true);
+  const double t_1 = now_us();
+  for (double& v : h->host_us) v = 0.0;
+  h->host_us[0] = t_1 - t_0;
   if (h->spec_cap > 0) {
     h->assume_frames(h->spec_cap);
     const int cap = h->maxFrm;
@@ -2168,13 +2182,17 @@ static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths
     int* pi = reinterpret_cast<int*>(pw + ncap);
     CK(cudaMemcpyAsync(pw, h->d_wav.p, ncap * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (frame_token) CK(cudaMemcpyAsync(pi, h->d_ftok.p, (size_t)cap * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const double t_2 = now_us();
     CK(cudaStreamSynchronize(h->stream));
+    const double t_3 = now_us();
+    h->host_us[1] = t_2 - t_1; h->host_us[2] = t_3 - t_2;
     REQUIRE(h->read_published_lengths(), VTTS_ERR_CUDA, "phase 1 finished without publishing the utterance lengths");
     const int real = h->h_frm_len[0];
     h->real_Tfrm = real; h->real_maxFrm = real;
     h->spec_learn();
     y_lengths[0] = real;
     *phase = 1;
+    h->host_us[5] = real <= cap ? 1.0 : 2.0;
     if (real <= cap) {
       ++h->spec_hits;
       h->last_graphed = true;
@@ -2185,6 +2203,7 @@ static void impl_infer(vtts_handle h, const int64_t* ids, const int64_t* lengths
       memcpy(wav, pw, (size_t)real * h->hop * sizeof(float));
       if (frame_token) memcpy(frame_token, pi, (size_t)real * sizeof(int));
       h->have_durations = false;
+      h->host_us[3] = now_us() - t_3; h->host_us[4] = now_us() - t_0;
       return;
     }
     ++h->spec_misses;                    // predicted bucket too small (the device-side lengths were clamped to it): true
@@ -2531,6 +2550,12 @@ int vtts_set_graphs(vtts_handle h, int enable) {
 }
 
 uint64_t vtts_graph_replays(vtts_handle h) { return h ? h->graph_replays : 0; }
+
+int vtts_host_timings(vtts_handle h, double* us, int n) {
+  if (!h || !us) return VTTS_ERR_INVALID;
+  for (int i = 0; i < n && i < 8; ++i) us[i] = h->host_us[i];
+  return VTTS_OK;
+}
 
 int vtts_speculation_stats(vtts_handle h, uint64_t* hits, uint64_t* misses) {
   if (!h || !hits || !misses) return VTTS_ERR_INVALID;

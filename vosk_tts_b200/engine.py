@@ -43,7 +43,7 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
            "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev",
-           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention", "vtts_speculation_stats"]
+           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention", "vtts_speculation_stats", "vtts_host_timings"]
 
 
 def lib_path():
@@ -116,6 +116,8 @@ def load_library(build_if_missing=True):
     lib.vtts_debug_attention.restype = i32
     lib.vtts_speculation_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.vtts_speculation_stats.restype = i32
+    lib.vtts_host_timings.argtypes = [vp, C.POINTER(C.c_double), i32]
+    lib.vtts_host_timings.restype = i32
     _LIB = lib
     return lib
 
@@ -382,6 +384,12 @@ class Engine:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._check(self.lib.vtts_speculation_stats(self.h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
+
+    def host_timings(self):
+        """Host-side microseconds of the last single-utterance infer call (see vtts_host_timings)."""
+        a = (C.c_double * 8)()
+        self._check(self.lib.vtts_host_timings(self.h, a, 8))
+        return [float(v) for v in a]
 
     def profile(self, enable):
         self._check(self.lib.vtts_profile(self.h, int(bool(enable))))
