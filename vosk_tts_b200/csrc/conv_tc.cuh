@@ -381,17 +381,22 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   //  128 KB of weights; the authoritative read stays after the wait)
   const bool peek_active = t0 < lens[b] * tb.rmul + P.in_extra;
   const int w_pre = (tb.wpre && peek_active) ? min(TC_WST, s_end - s_beg) : 0;
-  auto issue_w = [&](int s) {
-    const int c = s / P.k, j = s - c * P.k;
-    const int wst = (s - s_beg) % TC_WST;
+  // (ring slots, use parities and the (chunk, tap) pair of a k-step are carried as counters: the ring depths are launch
+  //  parameters, and run-time divisions in the single producer / issuer threads cost ~8 % on machine-filling launches)
+  auto issue_w = [&](int c, int j, int wst) {
     uint8_t* wb = smem_w + wst * NP * B_BYTES;
     mbar_expect_tx(&w_full[wst], NP * B_BYTES);
     tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
   };
-  if (warp == 0 && lane == 0)
-    for (int i = 0; i < w_pre; ++i) issue_w(s_beg + i);
+  if (warp == 0 && lane == 0) {
+    int c = s_beg / P.k, j = s_beg - c * P.k;
+    for (int i = 0; i < w_pre; ++i) {          // w_pre <= TC_WST: slot == i
+      issue_w(c, j, i);
+      if (++j == P.k) { j = 0; ++c; }
+    }
+  }
   // everything above touched only this CTA's resources and constants; from here on the producer kernel's results are needed
   PDL_WAIT();
   const int L = lens[b] * tb.rmul + P.in_extra;
@@ -408,11 +413,12 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       const uint32_t a_tx = (uint32_t)NP * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per set of planes
+      int c = s_beg / P.k, j = s_beg - c * P.k;
+      int ast = 0, a_use = 0, a_cnt = 0, wst = 0, w_use = 0;    // ring slot / times the ring wrapped / steps since the last A tile
       for (int s = s_beg; s < s_end; ++s) {
-        const int c = s / P.k, j = s - c * P.k;
         const int ls = s - s_beg;                              // ring positions count this CTA's own steps
-        if (ls % a_per == 0) {
-          const int ai = ls / a_per, ast = ai % TC_AST, use = ai / TC_AST;
+        if (a_cnt == 0) {
+          const int use = a_use;
           if (use > 0) mbar_wait(&a_empty[ast], (use - 1) & 1);
           uint8_t* ab = smem + ast * NP * A_BYTES;
           mbar_expect_tx(&a_full[ast], a_tx);
@@ -428,12 +434,15 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
             tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
             if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]);
           }
+          if (++ast == TC_AST) { ast = 0; ++a_use; }
         }
+        if (++a_cnt == a_per) a_cnt = 0;
         if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
-          const int wst = ls % TC_WST, wuse = ls / TC_WST;
-          if (wuse > 0) mbar_wait(&w_empty[wst], (wuse - 1) & 1);
-          issue_w(s);
+          if (w_use > 0) mbar_wait(&w_empty[wst], (w_use - 1) & 1);
+          issue_w(c, j, wst);
         }
+        if (++wst == TC_WST) { wst = 0; ++w_use; }
+        if (++j == P.k) { j = 0; ++c; }
         if (ls == 0) TC_STAMP(2);
       }
       TC_STAMP(3);
@@ -442,13 +451,12 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
+      int c = s_beg / P.k, j = s_beg - c * P.k;
+      int ast = 0, a_use = 0, a_cnt = 0, wst = 0, w_use = 0;
       for (int s = s_beg; s < s_end; ++s) {
-        const int c = s / P.k, j = s - c * P.k;
         const int ls = s - s_beg;
-        const int ai = ls / a_per, ast = ai % TC_AST;
-        if (ls % a_per == 0) mbar_wait(&a_full[ast], (ai / TC_AST) & 1);
-        const int wst = ls % TC_WST;
-        mbar_wait(&w_full[wst], (ls / TC_WST) & 1);
+        if (a_cnt == 0) mbar_wait(&a_full[ast], a_use & 1);
+        mbar_wait(&w_full[wst], w_use & 1);
         if (ls == 0) TC_STAMP(4);
         tc_fence_after();
         const uint32_t abase = smem_u32(smem + ast * NP * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
@@ -478,11 +486,14 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           }
         }
         umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
-        if ((ls + 1) % a_per == 0) {                           // ... and the activation tile after its last tap
+        if (++wst == TC_WST) { wst = 0; ++w_use; }
+        if (++a_cnt == a_per) {                                // ... and the activation tile after its last tap
           if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
           else umma_commit(&a_empty[ast]);
+          a_cnt = 0;
+          if (++ast == TC_AST) { ast = 0; ++a_use; }
         }
-        (void)c;
+        if (++j == P.k) { j = 0; ++c; }
       }
       umma_commit(tmem_full);                 // accumulator complete
       TC_STAMP(5);
