@@ -74,6 +74,9 @@ struct TcBatch {
   int np;       // operand planes: 2 = (hi, lo), three MMAs per K16 slice (lo*hi + hi*lo + hi*hi, ~2^-17 relative);
                 //   3 = (hi, mid, lo), six MMAs (hl + lh + mm + mh + hm + hh): products exact to the last fp32 bit
   int ast, wst; // ring depths (activation / weight tiles) for this launch
+  int coal;     // 1: launches without split-K finish their tiles through the shared-memory transposition (coalesced rows)
+  int persist;  // 1: 1-D grid of resident CTAs walking the (gx, gy, gz) tile space (machine-filling launches)
+  int gx, gy, gz;
   int split;    // cluster split-K: `split` CTAs (cluster dims (1,1,split)) each run a contiguous range of the k-steps of one
                 //    output tile, exchange partial accumulators through distributed shared memory and each finish
                 //    64/split of the tile's columns (reduce-scatter; fixed summation order => deterministic).  1 = off
@@ -250,6 +253,123 @@ __device__ __forceinline__ void tc_finish_cols(const TcProblem& P, float (&v)[EN
   }
 }
 
+// Coalesced finish of one epilogue pass (S == 1).  A TMEM lane is a tile row, so after tcgen05.ld a thread owns 64 columns of
+// ONE row: stores straight from that layout make every warp instruction touch 32 different rows (32 L1 wavefronts for
+// 512 bytes; ncu on the batched decoder launches: the LSU, not the tensor pipe or HBM, bounded the tile).  The warp
+// therefore parks its 32 x 64 block in shared memory (16-byte chunks XOR-swizzled by row, conflict-free both ways) and
+// reads it back with 16 lanes per row: a warp instruction then covers two rows x 256 contiguous bytes, the residual
+// is loaded and the fp32 rows / bf16 planes are stored as full lines.  `stg` = this warp's [32][64] floats.
+template <bool GATE>
+__device__ __forceinline__ void tc_finish_rows(const TcProblem& P, const float* stg, const float* bias_t, int cofs, int trow0, int L,
+                                               long out_base, int lane, const float4 (&rq)[16], bool r_pre) {
+  constexpr int NO = GATE ? 2 : 4;                    // outputs per thread (a gate pair (2i, 2i+1) makes one channel)
+  const int half = lane >> 4, cj = lane & 15;
+  const int c = cofs + cj * 4;
+  const int oc = GATE ? (c >> 1) : c;
+  const int nvalid = min(NO, (GATE ? (P.Cout >> 1) : P.Cout) - oc);
+  if (nvalid <= 0) return;
+  const float4 b4 = *reinterpret_cast<const float4*>(bias_t + cj * 4);
+  const bool relu = (P.epi & TCE_RELU) != 0;
+  const bool full = nvalid == NO;
+  const bool y_vec = full && ((P.ldy | P.yoff) & (NO - 1)) == 0;
+  const bool r_vec = full && ((P.ldr | P.roff) & (NO - 1)) == 0;
+  const bool p_vec = full && ((P.ldp | P.poff) & (NO - 1)) == 0;
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int r = it * 2 + half;
+    const int t = trow0 + r;
+    if (t >= L) break;
+    const long orow = out_base + (long)t * P.out_mul + P.out_add;
+    float4 a = *reinterpret_cast<const float4*>(stg + r * 64 + ((cj ^ (r & 7)) << 2));
+    a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+    float u[4];
+    if (GATE) {
+      u[0] = tanhf(a.x) * (1.f / (1.f + expf(-a.y)));
+      u[1] = tanhf(a.z) * (1.f / (1.f + expf(-a.w)));
+      u[2] = u[3] = 0.f;
+    } else {
+      u[0] = a.x; u[1] = a.y; u[2] = a.z; u[3] = a.w;
+    }
+#pragma unroll
+    for (int e = 0; e < NO; ++e) {
+      float q = u[e];
+      if (relu) q = fmaxf(q, 0.f);
+      u[e] = q * P.alpha;
+    }
+    if (r_pre) {
+      u[0] += rq[it].x; u[1] += rq[it].y; u[2] += rq[it].z; u[3] += rq[it].w;
+    } else if (P.res) {
+      const float* rp = P.res + orow * (long)P.ldr + P.roff + oc;
+      if (r_vec) {
+        if (GATE) { const float2 q2 = *reinterpret_cast<const float2*>(rp); u[0] += q2.x; u[1] += q2.y; }
+        else { const float4 q4 = *reinterpret_cast<const float4*>(rp); u[0] += q4.x; u[1] += q4.y; u[2] += q4.z; u[3] += q4.w; }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NO; ++e) if (e < nvalid) u[e] += rp[e];
+      }
+    }
+    if (P.y) {
+      float* yr = P.y + orow * (long)P.ldy + P.yoff + oc;
+      if (y_vec) {
+        if (GATE) *reinterpret_cast<float2*>(yr) = make_float2(u[0], u[1]);
+        else *reinterpret_cast<float4*>(yr) = make_float4(u[0], u[1], u[2], u[3]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < NO; ++e) if (e < nvalid) yr[e] = u[e];
+      }
+    }
+    if (P.p_hi) {
+      const long po = orow * (long)P.ldp + P.poff + oc;
+      __align__(8) __nv_bfloat16 hb[4], lb[4], mb[4];
+#pragma unroll
+      for (int e = 0; e < NO; ++e) {
+        float q = u[e];
+        q = q > 0.f ? q : q * P.pl_slope;
+        if (P.p_mid) split_bf16_3(q, hb[e], mb[e], lb[e]);
+        else split_bf16(q, hb[e], lb[e]);
+      }
+      if (p_vec) {
+        if (GATE) {
+          *reinterpret_cast<uint32_t*>(P.p_hi + po) = *reinterpret_cast<const uint32_t*>(hb);
+          *reinterpret_cast<uint32_t*>(P.p_lo + po) = *reinterpret_cast<const uint32_t*>(lb);
+          if (P.p_mid) *reinterpret_cast<uint32_t*>(P.p_mid + po) = *reinterpret_cast<const uint32_t*>(mb);
+        } else {
+          *reinterpret_cast<uint2*>(P.p_hi + po) = *reinterpret_cast<const uint2*>(hb);
+          *reinterpret_cast<uint2*>(P.p_lo + po) = *reinterpret_cast<const uint2*>(lb);
+          if (P.p_mid) *reinterpret_cast<uint2*>(P.p_mid + po) = *reinterpret_cast<const uint2*>(mb);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < NO; ++e)
+          if (e < nvalid) {
+            P.p_hi[po + e] = hb[e]; P.p_lo[po + e] = lb[e];
+            if (P.p_mid) P.p_mid[po + e] = mb[e];
+          }
+      }
+    }
+  }
+}
+
+// residual of the 16 (row, 4-column) units tc_finish_rows<false> handles in this thread, requested in one go (the loads
+// are in flight while the mainloop of the tile still runs).  Returns false when the vector path does not apply.
+__device__ __forceinline__ bool tc_prefetch_res_rows(const TcProblem& P, float4 (&rq)[16], int cofs, int trow0, int L, long out_base, int lane) {
+  if (!P.res || (P.epi & TCE_GATE) || ((P.ldr | P.roff) & 3) != 0) return false;
+  const int half = lane >> 4, cj = lane & 15;
+  const int c = cofs + cj * 4;
+  const bool colok = c + 4 <= P.Cout;
+#pragma unroll
+  for (int it = 0; it < 16; ++it) {
+    const int t = trow0 + it * 2 + half;
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (colok && t < L) {
+      const long orow = out_base + (long)t * P.out_mul + P.out_add;
+      q4 = *reinterpret_cast<const float4*>(P.res + orow * (long)P.ldr + P.roff + c);
+    }
+    rq[it] = q4;
+  }
+  return true;
+}
+
 // Split-K tail of one epilogue thread (= one tile row).  The tile's BN columns are cut into SS slices of W = BN/SS;
 // slice q is finished by CTA q.  tc_split_send pushes the slices contained in one 64-column accumulator pass into the
 // owners' staging buffers [src CTA][row][W] (this CTA's own slice included, so no register array is indexed dynamically);
@@ -308,11 +428,26 @@ __device__ __forceinline__ void tc_split_tail(const TcProblem& P, LoadAcc&& load
 }
 
 template <int BN>
-constexpr int tc_smem_bytes(int a_bytes, int np = 2, int ast = tc_ast<BN>(), int wst = tc_wst<BN>()) {
-  return ast * np * a_bytes + wst * np * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
+constexpr int tc_smem_bytes(int a_bytes, int np = 2, int ast = tc_ast<BN>(), int wst = tc_wst<BN>(), int stage_bytes = 0) {
+  return ast * np * a_bytes + wst * np * BN * TC_BK * 2 + 1024 /*alignment slack*/ + 256 /*barriers*/ + 2 * BN * 4 /*bias, two tiles in flight*/ +
+         stage_bytes /*epilogue transposition buffer of the S == 1 launches*/;
 }
+constexpr int TC_STAGE_BYTES = 4 * 32 * 64 * 4;   // four epilogue warps x [32 rows][64 columns] fp32
 constexpr int TC_MAXST = 4;   // barrier slots per ring
 
+// One output tile of a launch: 128 rows x BN channels of problem `P` in utterance `b`.
+struct TcTile {
+  const TcProblem* P;
+  int b, co0, t0, sp;
+  bool valid;       // the problem has this channel tile (grouped problems may differ in Cout)
+};
+
+// Launch shapes.  (1) one tile per CTA, grid (row tiles, channel tiles, utterances x problems x split): the latency-bound
+// single-utterance launches, with cluster split-K.  (2) tb.persist: a 1-D grid of one CTA per SM walks the same tile space
+// with a stride of gridDim.x; the accumulator is double-buffered in TMEM (2 x BN columns), the operand rings and their
+// parities run on across tiles, so tile i's epilogue (TMEM -> registers -> global) overlaps tile i+1's TMA + MMA mainloop
+// and the per-CTA prologue (barrier init, TMEM allocation, descriptor prefetch, pipeline fill) is paid once per SM
+// instead of once per tile.
 template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
@@ -320,18 +455,35 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const int TC_AST = tb.ast, TC_WST = tb.wst, NP = tb.np;
   PDL_LAUNCH();
   if (threadIdx.x == 0) TC_STAMP(0);
-  // cluster split-K ways; blockIdx.z = (b * n + problem) * S + rank.  The non-split instantiation carries none of the
+  // cluster split-K ways; z = (b * n + problem) * S + rank.  The non-split instantiation carries none of the
   // exchange code (measured: 6 % faster on machine-filling launches)
   const int S = SPLIT ? tb.split : 1;
-  const int zi = blockIdx.z / S, sp = blockIdx.z - zi * S;
-  const int pi = zi % tb.n;
-  const int b = zi / tb.n;
-  const TcProblem& P = tb.p[pi];
-  const int co0 = blockIdx.y * BN;
-  if (co0 >= P.Cout) return;
-  const int t0 = blockIdx.x * TC_BM;
+  const bool persist = !SPLIT && tb.persist != 0;
   const int A_BYTES = tb.a_bytes;
   const bool tall = tb.tall != 0;
+  const int ntiles = persist ? tb.gx * tb.gy * tb.gz : 1;
+  const int tstride = persist ? (int)gridDim.x : 1;
+  const int tile0 = persist ? (int)blockIdx.x : 0;
+  auto decode = [&](int tile) {
+    int bx, by, bz;
+    if (persist) {
+      bx = tile % tb.gx;
+      const int r = tile / tb.gx;
+      by = r % tb.gy;
+      bz = r / tb.gy;
+    } else {
+      bx = blockIdx.x; by = blockIdx.y; bz = blockIdx.z;
+    }
+    TcTile t;
+    const int zi = bz / S;
+    t.sp = bz - zi * S;
+    t.P = &tb.p[zi % tb.n];
+    t.b = zi / tb.n;
+    t.co0 = by * BN;
+    t.t0 = bx * TC_BM;
+    t.valid = t.co0 < t.P->Cout;
+    return t;
+  };
 
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -340,31 +492,35 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   uint64_t* a_empty = a_full + TC_MAXST;
   uint64_t* w_full = a_empty + TC_MAXST;
   uint64_t* w_empty = w_full + TC_MAXST;
-  uint64_t* tmem_full = w_empty + TC_MAXST;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [BN]
+  uint64_t* acc_full = w_empty + TC_MAXST;          // [2] accumulator buffer complete (tcgen05.commit)
+  uint64_t* acc_empty = acc_full + 2;               // [2] accumulator buffer drained by the 4 epilogue warps
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);          // [2][BN]
+  float* stage_t = bias_s + 2 * BN;                                 // [4][32][64] (launches without split-K only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nsteps_all = (P.Cin / TC_BK) * P.k;
-  const int s_beg = (int)((long)nsteps_all * sp / S), s_end = (int)((long)nsteps_all * (sp + 1) / S);   // this CTA's k-steps
-  const int a_per = tall ? P.k : 1;                    // k-steps sharing one activation tile (tall => S == 1)
+  const TcTile first = decode(tile0);
+  const uint32_t tmem_cols = persist ? 2u * BN : (uint32_t)BN;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], (uint32_t)tb.cn); }
     for (int s = 0; s < TC_WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_lo)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_hi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_lo)) : "memory");
-    if (NP == 3) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_mid)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_mid)) : "memory");
+    for (int q = 0; q < (persist ? tb.n : 1); ++q) {
+      const TcProblem& Q = persist ? tb.p[q] : *first.P;
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.a_hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.a_lo)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.w_hi)) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.w_lo)) : "memory");
+      if (NP == 3) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.a_mid)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&Q.w_mid)) : "memory");
+      }
     }
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -379,187 +535,266 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   // (lens/offs are final before any graph that reads them starts -- host copies or the previous phase's graph -- so the
   //  peek below only decides whether prefetching is worth it: idle CTAs of ragged batches must not fetch and then drain
   //  128 KB of weights; the authoritative read stays after the wait)
-  const bool peek_active = t0 < lens[b] * tb.rmul + P.in_extra;
-  const int w_pre = (tb.wpre && peek_active) ? min(TC_WST, s_end - s_beg) : 0;
-  // (ring slots, use parities and the (chunk, tap) pair of a k-step are carried as counters: the ring depths are launch
-  //  parameters, and run-time divisions in the single producer / issuer threads cost ~8 % on machine-filling launches)
-  auto issue_w = [&](int c, int j, int wst) {
+  int w_pre = 0;
+  auto issue_w = [&](const TcProblem& P, int co0, int c, int j, int wst) {
     uint8_t* wb = smem_w + wst * NP * B_BYTES;
     mbar_expect_tx(&w_full[wst], NP * B_BYTES);
     tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
   };
-  if (warp == 0 && lane == 0) {
-    int c = s_beg / P.k, j = s_beg - c * P.k;
-    for (int i = 0; i < w_pre; ++i) {          // w_pre <= TC_WST: slot == i
-      issue_w(c, j, i);
-      if (++j == P.k) { j = 0; ++c; }
+  if (!persist && first.valid) {
+    const TcProblem& P = *first.P;
+    const int nsteps_all = (P.Cin / TC_BK) * P.k;
+    const int s_beg = (int)((long)nsteps_all * first.sp / S), s_end = (int)((long)nsteps_all * (first.sp + 1) / S);
+    const bool peek_active = first.t0 < lens[first.b] * tb.rmul + P.in_extra;
+    w_pre = (tb.wpre && peek_active) ? min(TC_WST, s_end - s_beg) : 0;
+    if (warp == 0 && lane == 0) {
+      int c = s_beg / P.k, j = s_beg - c * P.k;
+      for (int i = 0; i < w_pre; ++i) {          // w_pre <= TC_WST: slot == i
+        issue_w(P, first.co0, c, j, i);
+        if (++j == P.k) { j = 0; ++c; }
+      }
     }
   }
   // everything above touched only this CTA's resources and constants; from here on the producer kernel's results are needed
   PDL_WAIT();
-  const int L = lens[b] * tb.rmul + P.in_extra;
-  const bool active = t0 < L;            // an idle CTA still has to release its TMEM columns below
-  const long in_base = (long)offs[b] * tb.rmul + (long)b * P.in_extra;
-  const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
   if (threadIdx.x == 0) TC_STAMP(1);
+  bool any_active = false;               // (split-K: the single tile of this CTA is active)
 
-  if (!active) {
-    // nothing to compute; the prefetched weight tiles must have landed before this CTA's shared memory is released
-    if (warp == 0 && lane == 0)
-      for (int i = 0; i < w_pre; ++i) mbar_wait(&w_full[i], 0);
-  } else if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    // (ring slots, use parities and the (chunk, tap) pair of a k-step are carried as counters: the ring depths are launch
+    //  parameters, and run-time divisions in the single producer / issuer threads cost ~8 % on machine-filling launches)
     if (lane == 0) {
-      const uint32_t a_tx = (uint32_t)NP * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per set of planes
-      int c = s_beg / P.k, j = s_beg - c * P.k;
-      int ast = 0, a_use = 0, a_cnt = 0, wst = 0, w_use = 0;    // ring slot / times the ring wrapped / steps since the last A tile
-      for (int s = s_beg; s < s_end; ++s) {
-        const int ls = s - s_beg;                              // ring positions count this CTA's own steps
-        if (a_cnt == 0) {
-          const int use = a_use;
-          if (use > 0) mbar_wait(&a_empty[ast], (use - 1) & 1);
-          uint8_t* ab = smem + ast * NP * A_BYTES;
-          mbar_expect_tx(&a_full[ast], a_tx);
-          const int row = (int)in_base + t0 - P.pad + (tall ? 0 : j * P.dil);
-          if (cn > 1) {
-            // this CTA fetches rows [crank, crank+1) * 128/cn of the tile and multicasts them to all cn CTAs
-            const int slice = TC_BM / cn;
-            const int soff = (int)crank * slice;
-            tma_load_2d_mc(ab + soff * 128, &P.a_hi, c * TC_BK, row + soff, &a_full[ast], cmask);
-            tma_load_2d_mc(ab + A_BYTES + soff * 128, &P.a_lo, c * TC_BK, row + soff, &a_full[ast], cmask);
-          } else {
-            tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
-            tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
-            if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]);
+      int ast = 0, a_use = 0, wst = 0, w_use = 0;    // ring slot / times the ring wrapped: run on across tiles
+      for (int tile = tile0; tile < ntiles; tile += tstride) {
+        const TcTile T = persist ? decode(tile) : first;
+        if (!T.valid) continue;
+        const TcProblem& P = *T.P;
+        const int L = lens[T.b] * tb.rmul + P.in_extra;
+        if (T.t0 >= L) {
+          // nothing to compute; prefetched weight tiles must have landed before this CTA's shared memory is released
+          for (int i = 0; i < w_pre; ++i) mbar_wait(&w_full[i], 0);
+          continue;
+        }
+        any_active = true;
+        const long in_base = (long)offs[T.b] * tb.rmul + (long)T.b * P.in_extra;
+        const int nsteps_all = (P.Cin / TC_BK) * P.k;
+        const int s_beg = (int)((long)nsteps_all * T.sp / S), s_end = (int)((long)nsteps_all * (T.sp + 1) / S);   // this CTA's k-steps
+        const int a_per = tall ? P.k : 1;                    // k-steps sharing one activation tile (tall => S == 1)
+        const uint32_t a_tx = (uint32_t)NP * (uint32_t)(tall ? (TC_BM + (P.k - 1) * P.dil) : TC_BM) * 128u;   // bytes TMA delivers per set of planes
+        int c = s_beg / P.k, j = s_beg - c * P.k;
+        int a_cnt = 0;                                         // steps since the last A tile
+        for (int s = s_beg; s < s_end; ++s) {
+          const int ls = s - s_beg;
+          if (a_cnt == 0) {
+            if (a_use > 0) mbar_wait(&a_empty[ast], (a_use - 1) & 1);
+            uint8_t* ab = smem + ast * NP * A_BYTES;
+            mbar_expect_tx(&a_full[ast], a_tx);
+            const int row = (int)in_base + T.t0 - P.pad + (tall ? 0 : j * P.dil);
+            if (cn > 1) {
+              // this CTA fetches rows [crank, crank+1) * 128/cn of the tile and multicasts them to all cn CTAs
+              const int slice = TC_BM / cn;
+              const int soff = (int)crank * slice;
+              tma_load_2d_mc(ab + soff * 128, &P.a_hi, c * TC_BK, row + soff, &a_full[ast], cmask);
+              tma_load_2d_mc(ab + A_BYTES + soff * 128, &P.a_lo, c * TC_BK, row + soff, &a_full[ast], cmask);
+            } else {
+              tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
+              tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
+              if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]);
+            }
+            if (++ast == TC_AST) { ast = 0; ++a_use; }
           }
-          if (++ast == TC_AST) { ast = 0; ++a_use; }
+          if (++a_cnt == a_per) a_cnt = 0;
+          if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
+            if (w_use > 0) mbar_wait(&w_empty[wst], (w_use - 1) & 1);
+            issue_w(P, T.co0, c, j, wst);
+          }
+          if (++wst == TC_WST) { wst = 0; ++w_use; }
+          if (++j == P.k) { j = 0; ++c; }
+          if (ls == 0) TC_STAMP(2);
         }
-        if (++a_cnt == a_per) a_cnt = 0;
-        if (ls >= w_pre) {                                     // (the first ring was requested before PDL_WAIT)
-          if (w_use > 0) mbar_wait(&w_empty[wst], (w_use - 1) & 1);
-          issue_w(c, j, wst);
-        }
-        if (++wst == TC_WST) { wst = 0; ++w_use; }
-        if (++j == P.k) { j = 0; ++c; }
-        if (ls == 0) TC_STAMP(2);
+        w_pre = 0;
+        TC_STAMP(3);
       }
-      TC_STAMP(3);
     }
+    any_active = __shfl_sync(0xffffffffu, (int)any_active, 0) != 0;
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
-      int c = s_beg / P.k, j = s_beg - c * P.k;
-      int ast = 0, a_use = 0, a_cnt = 0, wst = 0, w_use = 0;
-      for (int s = s_beg; s < s_end; ++s) {
-        const int ls = s - s_beg;
-        if (a_cnt == 0) mbar_wait(&a_full[ast], a_use & 1);
-        mbar_wait(&w_full[wst], w_use & 1);
-        if (ls == 0) TC_STAMP(4);
-        tc_fence_after();
-        const uint32_t abase = smem_u32(smem + ast * NP * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
-        const uint32_t wbase = smem_u32(smem_w + wst * NP * B_BYTES);
-        const uint64_t ahi = umma_desc_sw128(abase, tb.baseoff), alo = umma_desc_sw128(abase + A_BYTES, tb.baseoff);
-        const uint64_t bhi = umma_desc_sw128(wbase), blo = umma_desc_sw128(wbase + B_BYTES);
-        if (NP == 3) {
-          // exact 3-way split: the six products that reach the last bit of an fp32 product, smallest first
-          const uint64_t ami = umma_desc_sw128(abase + 2 * A_BYTES), bmi = umma_desc_sw128(wbase + 2 * B_BYTES);
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
-            umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, (ls | kk) ? 1u : 0u);
-            umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, 1u);
-            umma_bf16(tmem_base, ami + adv, bmi + adv, idesc, 1u);
-            umma_bf16(tmem_base, ami + adv, bhi + adv, idesc, 1u);
-            umma_bf16(tmem_base, ahi + adv, bmi + adv, idesc, 1u);
-            umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
-          }
-        } else {
-#pragma unroll
-          for (int kk = 0; kk < TC_BK / 16; ++kk) {
-            const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
-            umma_bf16(tmem_base, alo + adv, bhi + adv, idesc, (ls | kk) ? 1u : 0u);
-            umma_bf16(tmem_base, ahi + adv, blo + adv, idesc, 1u);
-            umma_bf16(tmem_base, ahi + adv, bhi + adv, idesc, 1u);
-          }
+      int ast = 0, a_use = 0, wst = 0, w_use = 0, lt = 0;
+      for (int tile = tile0; tile < ntiles; tile += tstride) {
+        const TcTile T = persist ? decode(tile) : first;
+        if (!T.valid) continue;
+        const TcProblem& P = *T.P;
+        const int L = lens[T.b] * tb.rmul + P.in_extra;
+        if (T.t0 >= L) continue;
+        any_active = true;
+        const int nsteps_all = (P.Cin / TC_BK) * P.k;
+        const int s_beg = (int)((long)nsteps_all * T.sp / S), s_end = (int)((long)nsteps_all * (T.sp + 1) / S);
+        const int a_per = tall ? P.k : 1;
+        const int buf = lt & 1;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+        if (lt >= 2) {                                          // the epilogue has drained this buffer's previous tile
+          mbar_wait(&acc_empty[buf], ((lt >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
-        if (++wst == TC_WST) { wst = 0; ++w_use; }
-        if (++a_cnt == a_per) {                                // ... and the activation tile after its last tap
-          if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
-          else umma_commit(&a_empty[ast]);
-          a_cnt = 0;
-          if (++ast == TC_AST) { ast = 0; ++a_use; }
+        int c = s_beg / P.k, j = s_beg - c * P.k;
+        int a_cnt = 0;
+        for (int s = s_beg; s < s_end; ++s) {
+          const int ls = s - s_beg;
+          if (a_cnt == 0) mbar_wait(&a_full[ast], a_use & 1);
+          mbar_wait(&w_full[wst], w_use & 1);
+          if (ls == 0) TC_STAMP(4);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(smem + ast * NP * A_BYTES) + (tall ? (uint32_t)(j * P.dil) * 128u : 0u);
+          const uint32_t wbase = smem_u32(smem_w + wst * NP * B_BYTES);
+          const uint64_t ahi = umma_desc_sw128(abase, tb.baseoff), alo = umma_desc_sw128(abase + A_BYTES, tb.baseoff);
+          const uint64_t bhi = umma_desc_sw128(wbase), blo = umma_desc_sw128(wbase + B_BYTES);
+          if (NP == 3) {
+            // exact 3-way split: the six products that reach the last bit of an fp32 product, smallest first
+            const uint64_t ami = umma_desc_sw128(abase + 2 * A_BYTES), bmi = umma_desc_sw128(wbase + 2 * B_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 16; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+              umma_bf16(tmem_acc, ahi + adv, blo + adv, idesc, (ls | kk) ? 1u : 0u);
+              umma_bf16(tmem_acc, alo + adv, bhi + adv, idesc, 1u);
+              umma_bf16(tmem_acc, ami + adv, bmi + adv, idesc, 1u);
+              umma_bf16(tmem_acc, ami + adv, bhi + adv, idesc, 1u);
+              umma_bf16(tmem_acc, ahi + adv, bmi + adv, idesc, 1u);
+              umma_bf16(tmem_acc, ahi + adv, bhi + adv, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < TC_BK / 16; ++kk) {
+              const uint64_t adv = (uint64_t)((kk * 32) >> 4);     // 16 bf16 = 32 bytes along K inside the swizzle atom
+              umma_bf16(tmem_acc, alo + adv, bhi + adv, idesc, (ls | kk) ? 1u : 0u);
+              umma_bf16(tmem_acc, ahi + adv, blo + adv, idesc, 1u);
+              umma_bf16(tmem_acc, ahi + adv, bhi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
+          if (++wst == TC_WST) { wst = 0; ++w_use; }
+          if (++a_cnt == a_per) {                                // ... and the activation tile after its last tap
+            if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
+            else umma_commit(&a_empty[ast]);
+            a_cnt = 0;
+            if (++ast == TC_AST) { ast = 0; ++a_use; }
+          }
+          if (++j == P.k) { j = 0; ++c; }
         }
-        if (++j == P.k) { j = 0; ++c; }
+        umma_commit(&acc_full[buf]);            // accumulator complete
+        ++lt;
+        TC_STAMP(5);
       }
-      umma_commit(tmem_full);                 // accumulator complete
-      TC_STAMP(5);
     }
+    any_active = __shfl_sync(0xffffffffu, (int)any_active, 0) != 0;
   } else {
     // ------------------------------------------------------------------ epilogue: 4 warps, one TMEM lane quadrant each
     // Everything that does not depend on the accumulator is fetched while the mainloop runs: bias (+ per-utterance
     // conditioning) into shared memory, the residual row into registers.
     const int quad = warp & 3;
     const int et = threadIdx.x - 64;                       // 0..127
-    if (et < BN) {
-      const int cc = co0 + et;
-      float bv = 0.f;
-      if (cc < P.Cout) {
-        bv = P.bias[cc];
-        if (P.cond) bv += P.cond[(long)b * P.cond_ld + cc];
+    int lt = 0;
+    for (int tile = tile0; tile < ntiles; tile += tstride) {
+      const TcTile T = persist ? decode(tile) : first;
+      if (!T.valid) continue;
+      const TcProblem& P = *T.P;
+      const int L = lens[T.b] * tb.rmul + P.in_extra;
+      if (T.t0 >= L) continue;
+      const int b = T.b, co0 = T.co0, sp = T.sp;
+      const int buf = lt & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
+      float* bias_t = bias_s + buf * BN;
+      const long out_base = (long)offs[b] * tb.rmul * P.out_mul + (long)b * P.out_seq_extra;
+      if (et < BN) {
+        const int cc = co0 + et;
+        float bv = 0.f;
+        if (cc < P.Cout) {
+          bv = P.bias[cc];
+          if (P.cond) bv += P.cond[(long)b * P.cond_ld + cc];
+        }
+        bias_t[et] = bv;
       }
-      bias_s[et] = bv;
-    }
-    const int t = t0 + quad * 32 + lane;
-    const bool rowok = t < L;
-    const long orow = out_base + (long)t * P.out_mul + P.out_add;
-    constexpr int EN = 64;                                 // columns handled per epilogue pass
-    float rr[EN];
-    if (S == 1) tc_load_res<EN>(P, rr, co0, orow, rowok);
-    asm volatile("bar.sync 1, 128;" ::: "memory");          // bias_s visible to the 4 epilogue warps
-    mbar_wait(tmem_full, 0);
-    if (threadIdx.x == 64) TC_STAMP(6);
-    tc_fence_after();
-    auto load_acc = [&](int eh, float (&v)[EN]) {           // 64 accumulator columns of this thread's TMEM lane
-      uint32_t rg[EN];
-#pragma unroll
-      for (int n0 = 0; n0 < EN; n0 += 16) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(eh * EN + n0);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-            : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
-              "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
-              "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
-            : "r"(taddr));
+      const int t = T.t0 + quad * 32 + lane;
+      const bool rowok = t < L;
+      const long orow = out_base + (long)t * P.out_mul + P.out_add;
+      constexpr int EN = 64;                                 // columns handled per epilogue pass
+      const bool coal = S == 1 && tb.coal != 0;
+      const int trow0 = T.t0 + quad * 32;
+      float rr[EN];                                          // residual, fetched while the mainloop runs: a row's 64 columns, or
+      float4 (&rq)[16] = *reinterpret_cast<float4 (*)[16]>(rr);   // (coalesced epilogue) 16 (row, 4-column) units
+      bool r_pre = false;
+      if (S == 1) {
+        if (coal) r_pre = tc_prefetch_res_rows(P, rq, co0, trow0, L, out_base, lane);
+        else tc_load_res<EN>(P, rr, co0, orow, rowok);
       }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // bias visible to the 4 epilogue warps (two tiles may be in flight:
+                                                              //  bias_s is double-buffered, tile i+2 is written after tile i+1's barrier)
+      mbar_wait(&acc_full[buf], (lt >> 1) & 1);
+      if (threadIdx.x == 64) TC_STAMP(6);
+      tc_fence_after();
+      auto load_acc = [&](int eh, float (&v)[EN]) {           // 64 accumulator columns of this thread's TMEM lane
+        uint32_t rg[EN];
 #pragma unroll
-      for (int i = 0; i < EN; ++i) v[i] = __uint_as_float(rg[i]);
-    };
-    if (S == 1) {
+        for (int n0 = 0; n0 < EN; n0 += 16) {
+          const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(eh * EN + n0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(rg[n0 + 0]), "=r"(rg[n0 + 1]), "=r"(rg[n0 + 2]), "=r"(rg[n0 + 3]), "=r"(rg[n0 + 4]), "=r"(rg[n0 + 5]),
+                "=r"(rg[n0 + 6]), "=r"(rg[n0 + 7]), "=r"(rg[n0 + 8]), "=r"(rg[n0 + 9]), "=r"(rg[n0 + 10]), "=r"(rg[n0 + 11]),
+                "=r"(rg[n0 + 12]), "=r"(rg[n0 + 13]), "=r"(rg[n0 + 14]), "=r"(rg[n0 + 15])
+              : "r"(taddr));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < EN; ++i) v[i] = __uint_as_float(rg[i]);
+      };
+      if (S == 1) {
+        const int npass = min(BN / EN, (P.Cout - co0 + EN - 1) / EN);
+        float* stg = stage_t + quad * (32 * 64);
+        const bool gate = (P.epi & TCE_GATE) != 0;
 #pragma unroll 1
-      for (int eh = 0; eh < BN / EN; ++eh) {
-        const int co0e = co0 + eh * EN;
-        if (co0e >= P.Cout) break;
-        if (eh > 0) tc_load_res<EN>(P, rr, co0e, orow, rowok);
-        float v[EN];
-        load_acc(eh, v);
+        for (int eh = 0; eh < npass; ++eh) {
+          const int co0e = co0 + eh * EN;
+          if (eh > 0) {
+            if (coal) r_pre = tc_prefetch_res_rows(P, rq, co0e, trow0, L, out_base, lane);
+            else tc_load_res<EN>(P, rr, co0e, orow, rowok);
+          }
+          float v[EN];
+          load_acc(eh, v);
+          if (persist && eh == npass - 1) {                    // accumulator buffer drained: the MMA warp may refill it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          }
+          if (coal) {
 #pragma unroll
-        for (int i = 0; i < EN; ++i) v[i] += bias_s[eh * EN + i];
-        if (rowok) tc_finish_cols<EN>(P, v, rr, co0e, orow);
+            for (int jq = 0; jq < EN / 4; ++jq)
+              *reinterpret_cast<float4*>(stg + lane * 64 + ((jq ^ (lane & 7)) << 2)) = make_float4(v[4 * jq], v[4 * jq + 1], v[4 * jq + 2], v[4 * jq + 3]);
+            __syncwarp();
+            if (gate) tc_finish_rows<true>(P, stg, bias_t + eh * EN, co0e, trow0, L, out_base, lane, rq, false);
+            else tc_finish_rows<false>(P, stg, bias_t + eh * EN, co0e, trow0, L, out_base, lane, rq, r_pre);
+            __syncwarp();                                      // the next pass (or tile) overwrites the block
+          } else {
+#pragma unroll
+            for (int i = 0; i < EN; ++i) v[i] += bias_t[eh * EN + i];
+            if (rowok) tc_finish_cols<EN>(P, v, rr, co0e, orow);
+          }
+        }
+      } else if constexpr (SPLIT) {
+        float* stage = reinterpret_cast<float*>(smem);       // [S][128][BN/S] fp32 (32 or 64 KB), aliases the activation ring
+        const int row = quad * 32 + lane;
+        if (S == 2) tc_split_tail<2, BN>(P, load_acc, stage, bias_t, sp, row, co0, orow, rowok);
+        else if (S == 4) tc_split_tail<4, BN>(P, load_acc, stage, bias_t, sp, row, co0, orow, rowok);
+        else tc_split_tail<8, BN>(P, load_acc, stage, bias_t, sp, row, co0, orow, rowok);
       }
-    } else if constexpr (SPLIT) {
-      float* stage = reinterpret_cast<float*>(smem);       // [S][128][BN/S] fp32 (32 or 64 KB), aliases the activation ring
-      const int row = quad * 32 + lane;
-      if (S == 2) tc_split_tail<2, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
-      else if (S == 4) tc_split_tail<4, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
-      else tc_split_tail<8, BN>(P, load_acc, stage, bias_s, sp, row, co0, orow, rowok);
+      ++lt;
     }
   }
-  if (S > 1 && active && warp < 2) {       // the producer and MMA warps take part in the two split-K cluster barriers
+  if (S > 1 && any_active && warp < 2) {   // the producer and MMA warps take part in the two split-K cluster barriers
     __syncwarp();
     cluster_sync_all();
     cluster_sync_all();
@@ -571,7 +806,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 

@@ -305,7 +305,7 @@ struct vtts_engine {
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
@@ -795,14 +795,30 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   TcBatch& tb = tc_batch;   // per-engine scratch (2.6 KB: kept off the stack frame of every caller)
   memset(&tb, 0, sizeof(tb));
   int maxCout = 0, maxL = 0, maxNR = TC_BM;
-  bool tall = tc_tall != 0;
+  // "Tall" activation tiles (one TMA box of 128 + (k-1)*dil rows per channel chunk, the taps read it through row-shifted
+  // descriptors) cut the L2 -> shared-memory traffic of a k-step from A + W to A/k + W.  On machine-filling launches the
+  // mainloop is bound by exactly that traffic (64 KB per k-step and SM at 128-wide tiles against 768 tensor-pipe cycles),
+  // so they use it by default (VTTS_TC_TALL: 0 auto, 1 always, -1 never); single-utterance launches prefer split-K.
+  bool np3 = false;
+  long grid_tiles = 0;
+  for (const TcSpec& q : ps) {
+    if (q.w.mid && q.in.mid) np3 = true;
+    grid_tiles += (long)((maxLen * rmul + q.in_extra + TC_BM - 1) / TC_BM) * ((q.Cout + BN - 1) / BN) * nB;
+  }
+  const bool big = tc_persist && grid_tiles > (long)tc_persist_min * n_sm;
+  bool tall = tc_tall > 0 || (tc_tall == 0 && big);
   for (const TcSpec& q : ps) {
     const int nr = TC_BM + (q.k - 1) * q.dil;
     if (nr > 192) tall = false;              // shared-memory budget of the activation ring (and TMA box <= 256)
     maxNR = std::max(maxNR, nr);
   }
-  if (BN == 128) tall = false;             // the 128-wide weight ring leaves no room for tall activation tiles
-  if (tall && tc_smem_bytes<64>((maxNR * 128 + 1023) / 1024 * 1024) > 227 * 1024) tall = false;   // (2-plane rings)
+  if (np3) tall = false;
+  if (tall) {
+    const int ab = (maxNR * 128 + 1023) / 1024 * 1024;
+    const int need = BN == 128 ? tc_smem_bytes<128>(ab, 2, 2, tc_coal ? 3 : tc_wst<128>(), tc_coal ? TC_STAGE_BYTES : 0)
+                               : tc_smem_bytes<64>(ab, 2, 2, tc_wst<64>(), tc_coal ? TC_STAGE_BYTES : 0);
+    if (need > 227 * 1024) tall = false;
+  }
   if (!tall) maxNR = TC_BM;
   // TMA multicast of the activation tile across the channel-tile CTAs of a cluster: only when every problem of the
   // launch has the same number of channel tiles (no CTA of a cluster may drop out) and the tile is not "tall"
@@ -856,8 +872,12 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   }
   if (np == 3) { tall = false; cn = 1; }
   tb.np = np;
-  tb.ast = np == 3 ? 2 : (BN == 128 ? tc_ast<128>() : tc_ast<64>());
-  tb.wst = np == 3 ? (BN == 128 ? 2 : 3) : (BN == 128 ? tc_wst<128>() : tc_wst<64>());
+  tb.ast = (np == 3 || tall) ? 2 : (BN == 128 ? tc_ast<128>() : tc_ast<64>());
+  // launches without split-K finish their tiles through a 32 KB transposition buffer (coalesced epilogue, conv_tc.cuh); with
+  // 128-wide channel tiles it takes the place of the fourth weight stage
+  tb.coal = (split == 1 && tc_coal) ? 1 : 0;
+  const int stage_bytes = tb.coal ? TC_STAGE_BYTES : 0;
+  tb.wst = np == 3 ? (BN == 128 ? 2 : 3) : (BN == 128 ? (tb.coal ? 3 : tc_wst<128>()) : tc_wst<64>());
   tb.split = split;
   tb.cn = cn;
   tb.tall = tall ? 1 : 0;
@@ -894,6 +914,13 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n * split);
   if (grid.x == 0) return;
   tb.wpre = (long)grid.x * grid.y * grid.z <= 148 ? 1 : 0;
+  // machine-filling launches: one resident CTA per SM walks the tile space (conv_tc.cuh)
+  tb.gx = (int)grid.x; tb.gy = (int)grid.y; tb.gz = (int)grid.z;
+  tb.persist = 0;
+  if (tc_persist && split == 1 && cn == 1 && !tb.wpre && (long)grid.x * grid.y * grid.z > (long)tc_persist_min * n_sm) {
+    tb.persist = 1;
+    grid = dim3((unsigned)n_sm, 1, 1);
+  }
   if (profiling) {
     if (tc_prof_used + 2 > tc_prof_ev.size()) {
       tc_prof_ev.resize(tc_prof_used + 2);
@@ -910,7 +937,8 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     cudaLaunchConfig_t lc;
     memset(&lc, 0, sizeof(lc));
     lc.gridDim = grid; lc.blockDim = dim3(TC_THREADS); lc.stream = stream;
-    lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes, tb.np, tb.ast, tb.wst) : tc_smem_bytes<64>(tb.a_bytes, tb.np, tb.ast, tb.wst);
+    lc.dynamicSmemBytes = BN == 128 ? tc_smem_bytes<128>(tb.a_bytes, tb.np, tb.ast, tb.wst, stage_bytes) : tc_smem_bytes<64>(tb.a_bytes, tb.np, tb.ast, tb.wst, stage_bytes);
+    REQUIRE(lc.dynamicSmemBytes <= 227 * 1024, VTTS_ERR_INVALID, "tensor-core conv: shared-memory budget exceeded");
     cudaLaunchAttribute at[2];
     int na = 0;
     if (cn > 1 || split > 1) {
@@ -2317,6 +2345,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
         fprintf(stderr, "[vtts] co-resident conv_tc clusters: BN64 %d/%d/%d  BN128 %d/%d/%d (S=2/4/8)\n", h->tc_cluster_cap[0][0], h->tc_cluster_cap[0][1],
                 h->tc_cluster_cap[0][2], h->tc_cluster_cap[1][0], h->tc_cluster_cap[1][1], h->tc_cluster_cap[1][2]);
     }
+    CK(cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& st : h->side) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -2341,6 +2370,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
+    if (const char* e = getenv("VTTS_TC_PERSIST")) h->tc_persist = atoi(e);                 // 0: one tile per CTA also on machine-filling launches
+    if (const char* e = getenv("VTTS_TC_COAL")) h->tc_coal = atoi(e);                       // 1: coalesced (transposed) epilogue on launches without split-K
+    if (const char* e = getenv("VTTS_TC_PERSIST_MIN")) h->tc_persist_min = std::max(1, atoi(e));   // tiles per SM from which the persistent grid is used
     if (const char* e = getenv("VTTS_MRF_BRANCH")) h->mrf_branch = atoi(e);
     if (const char* e = getenv("VTTS_MRF_HEAVY_FIRST")) h->mrf_heavy_first = atoi(e);
     if (const char* e = getenv("VTTS_WN_FUSED")) h->wn_fused = atoi(e);
