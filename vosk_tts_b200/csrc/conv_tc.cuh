@@ -74,6 +74,7 @@ struct TcBatch {
   int np;       // operand planes: 2 = (hi, lo), three MMAs per K16 slice (lo*hi + hi*lo + hi*hi, ~2^-17 relative);
                 //   3 = (hi, mid, lo), six MMAs (hl + lh + mm + mh + hm + hh): products exact to the last fp32 bit
   int ast, wst; // ring depths (activation / weight tiles) for this launch
+  int dbgskip;  // tuning experiments (timing only, wrong results): 1 = no epilogue stores, 2 = no MMAs issued, 4 = no residual loads
   int coal;     // 1: launches without split-K finish their tiles through the shared-memory transposition (coalesced rows)
   int persist;  // 1: 1-D grid of resident CTAs walking the (gx, gy, gz) tile space (machine-filling launches)
   int gx, gy, gz;
@@ -653,7 +654,8 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           const uint32_t wbase = smem_u32(smem_w + wst * NP * B_BYTES);
           const uint64_t ahi = umma_desc_sw128(abase, tb.baseoff), alo = umma_desc_sw128(abase + A_BYTES, tb.baseoff);
           const uint64_t bhi = umma_desc_sw128(wbase), blo = umma_desc_sw128(wbase + B_BYTES);
-          if (NP == 3) {
+          if (tb.dbgskip & 2) {
+          } else if (NP == 3) {
             // exact 3-way split: the six products that reach the last bit of an fp32 product, smallest first
             const uint64_t ami = umma_desc_sw128(abase + 2 * A_BYTES), bmi = umma_desc_sw128(wbase + 2 * B_BYTES);
 #pragma unroll
@@ -729,7 +731,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
       bool r_pre = false;
       if (S == 1) {
         if (coal) r_pre = tc_prefetch_res_rows(P, rq, co0, trow0, L, out_base, lane);
-        else tc_load_res<EN>(P, rr, co0, orow, rowok);
+        else tc_load_res<EN>(P, rr, co0, orow, rowok && !(tb.dbgskip & 4));
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");          // bias visible to the 4 epilogue warps (two tiles may be in flight:
                                                               //  bias_s is double-buffered, tile i+2 is written after tile i+1's barrier)
@@ -761,7 +763,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           const int co0e = co0 + eh * EN;
           if (eh > 0) {
             if (coal) r_pre = tc_prefetch_res_rows(P, rq, co0e, trow0, L, out_base, lane);
-            else tc_load_res<EN>(P, rr, co0e, orow, rowok);
+            else tc_load_res<EN>(P, rr, co0e, orow, rowok && !(tb.dbgskip & 4));
           }
           float v[EN];
           load_acc(eh, v);
@@ -781,7 +783,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           } else {
 #pragma unroll
             for (int i = 0; i < EN; ++i) v[i] += bias_t[eh * EN + i];
-            if (rowok) tc_finish_cols<EN>(P, v, rr, co0e, orow);
+            if (rowok && !(tb.dbgskip & 1)) tc_finish_cols<EN>(P, v, rr, co0e, orow);
           }
         }
       } else if constexpr (SPLIT) {
@@ -814,62 +816,78 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
 // fp32 rows -> split-bf16 planes (optionally through leaky-relu and the ReflectionPad1d((1,0)) row shift of
 // models.py:1039) for tensors that were not produced by a tensor-core epilogue.
 // ------------------------------------------------------------------------------------------------
-__global__ void split_planes_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    int ldp, int C, float slope, int reflect, int rmul, const int* __restrict__ lens,
-                                    const int* __restrict__ offs) {
+// Row blocking of the elementwise plane kernels: a block of EW_THREADS threads covers EW_ROWS consecutive rows of one
+// utterance, C/4 threads per row (one block per row left most of a batched launch in block-scheduling overhead:
+// mrf_mean_planes 8.1 ms of a 70 ms batch-64 step, profiles/r2_launches_batch64.csv).
+constexpr int EW_THREADS = 256;
+constexpr int EW_ROWS = 16;
+
+__global__ void __launch_bounds__(EW_THREADS)
+split_planes_kernel(const float* __restrict__ x, int ldx, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                    int ldp, int C, float slope, int reflect, int rmul, const int* __restrict__ lens,
+                    const int* __restrict__ offs) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.y;
   const int Lphys = lens[b] * rmul;
   const int L = Lphys + (reflect ? 1 : 0);
-  const int p = blockIdx.x;
-  if (p >= L) return;
-  const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
-  const long irow = (long)offs[b] * rmul + pr;
-  const long orow = (long)offs[b] * rmul + (reflect ? b : 0) + p;
-  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+  const int p0 = blockIdx.x * EW_ROWS;
+  if (p0 >= L) return;
+  const int nq = C >> 2;                               // float4 units per row
+  const int nrow = min(EW_ROWS, L - p0);
+  const long base = (long)offs[b] * rmul;
+  for (int u = threadIdx.x; u < nrow * nq; u += EW_THREADS) {
+    const int r = u / nq, c = (u - r * nq) << 2;
+    const int p = p0 + r;
+    const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
+    const long irow = base + pr;
+    const long orow = base + (reflect ? b : 0) + p;
     const float4 v = *reinterpret_cast<const float4*>(x + irow * ldx + c);
     const float f[4] = {v.x, v.y, v.z, v.w};
     __align__(8) __nv_bfloat16 hb[4], lb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float u = f[i] > 0.f ? f[i] : f[i] * slope;
-      split_bf16(u, hb[i], lb[i]);
+      const float q = f[i] > 0.f ? f[i] : f[i] * slope;
+      split_bf16(q, hb[i], lb[i]);
     }
     *reinterpret_cast<uint2*>(hi + orow * ldp + c) = *reinterpret_cast<const uint2*>(hb);
     *reinterpret_cast<uint2*>(lo + orow * ldp + c) = *reinterpret_cast<const uint2*>(lb);
   }
 }
 
-
-// MRF mean (models.py:1030-1036) that also emits the split-bf16 planes of leaky_relu(mean) for the next tensor-core
-// conv; with `reflect` the planes are written one row down and row 0 repeats row 1 (ReflectionPad1d((1,0))).
-__global__ void mrf_mean_planes_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c3, int n,
-                                       float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C,
-                                       float slope, int reflect, int rmul, const int* __restrict__ lens, const int* __restrict__ offs) {
+// mean of the resblock outputs of an MRF stage (models.py: xs / num_kernels) -> fp32 rows (optional) + planes of lrelu(mean)
+__global__ void __launch_bounds__(EW_THREADS)
+mrf_mean_planes_kernel(const float* __restrict__ a, const float* __restrict__ b2, const float* __restrict__ c3, int n,
+                       float* __restrict__ out, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int C,
+                       float slope, int reflect, int rmul, const int* __restrict__ lens, const int* __restrict__ offs) {
   PDL_LAUNCH();
   PDL_WAIT();
   const int b = blockIdx.y;
   const int Lphys = lens[b] * rmul;
   const int L = Lphys + (reflect ? 1 : 0);
-  const int p = blockIdx.x;
-  if (p >= L) return;
-  const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
-  const long irow = (long)offs[b] * rmul + pr;
-  const long orow = (long)offs[b] * rmul + (reflect ? b : 0) + p;
+  const int p0 = blockIdx.x * EW_ROWS;
+  if (p0 >= L) return;
+  const int nq = C >> 2;
+  const int nrow = min(EW_ROWS, L - p0);
+  const long base = (long)offs[b] * rmul;
   const float d = (float)n;
-  for (int c = threadIdx.x * 4; c < C; c += blockDim.x * 4) {
+  for (int u = threadIdx.x; u < nrow * nq; u += EW_THREADS) {
+    const int r = u / nq, c = (u - r * nq) << 2;
+    const int p = p0 + r;
+    const int pr = reflect ? (p == 0 ? 1 : p - 1) : p;
+    const long irow = base + pr;
+    const long orow = base + (reflect ? b : 0) + p;
     float4 s = *reinterpret_cast<const float4*>(a + irow * C + c);
-    if (n > 1) { const float4 u = *reinterpret_cast<const float4*>(b2 + irow * C + c); s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
-    if (n > 2) { const float4 u = *reinterpret_cast<const float4*>(c3 + irow * C + c); s.x += u.x; s.y += u.y; s.z += u.z; s.w += u.w; }
+    if (n > 1) { const float4 q = *reinterpret_cast<const float4*>(b2 + irow * C + c); s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+    if (n > 2) { const float4 q = *reinterpret_cast<const float4*>(c3 + irow * C + c); s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
     s.x /= d; s.y /= d; s.z /= d; s.w /= d;
     if (out && (!reflect || p >= 1)) *reinterpret_cast<float4*>(out + irow * C + c) = s;
     const float f[4] = {s.x, s.y, s.z, s.w};
     __align__(8) __nv_bfloat16 hb[4], lb[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float u = f[i] > 0.f ? f[i] : f[i] * slope;
-      split_bf16(u, hb[i], lb[i]);
+      const float q = f[i] > 0.f ? f[i] : f[i] * slope;
+      split_bf16(q, hb[i], lb[i]);
     }
     *reinterpret_cast<uint2*>(hi + orow * C + c) = *reinterpret_cast<const uint2*>(hb);
     *reinterpret_cast<uint2*>(lo + orow * C + c) = *reinterpret_cast<const uint2*>(lb);

@@ -305,7 +305,7 @@ struct vtts_engine {
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
@@ -882,6 +882,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.cn = cn;
   tb.tall = tall ? 1 : 0;
   tb.baseoff = tc_baseoff;
+  tb.dbgskip = tc_dbgskip;
   tb.a_bytes = (maxNR * 128 + 1023) / 1024 * 1024;
   for (size_t i = 0; i < ps.size(); ++i) {
     const TcSpec& q = ps[i];
@@ -1248,8 +1249,8 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo, bool pz_rea
   const std::vector<Planes>&st_px = dcp.px, &st_nxt = dcp.nxt;
   const std::vector<std::vector<Planes>>&st_pj = dcp.pj, &st_pt = dcp.pt;
   if (!pz_ready) {
-    dim3 g(maxFrm, B);
-    klaunch(split_planes_kernel, dim3(g), dim3(64), (size_t)(0), z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
+    dim3 g((maxFrm + EW_ROWS - 1) / EW_ROWS, B);
+    klaunch(split_planes_kernel, dim3(g), dim3(EW_THREADS), (size_t)(0), z, I, pz.hi, pz.lo, I, I, 1.f, 0, 1, fl, fo);
     CK(cudaGetLastError());
     ++launches;
   }
@@ -1345,8 +1346,8 @@ void vtts_engine::decoder_tc(float* z, const int* fl, const int* fo, bool pz_rea
     const bool last = (i + 1 == c.n_upsamples);
     Planes nxt = st_nxt[i];
     {
-      dim3 g(maxFrm * rm + (last ? 1 : 0), B);
-      klaunch(mrf_mean_planes_kernel, dim3(g), dim3(32), (size_t)(0), xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
+      dim3 g((maxFrm * rm + (last ? 1 : 0) + EW_ROWS - 1) / EW_ROWS, B);
+      klaunch(mrf_mean_planes_kernel, dim3(g), dim3(EW_THREADS), (size_t)(0), xj[0], nk > 1 ? xj[1] : nullptr, nk > 2 ? xj[2] : nullptr, std::min(nk, 3),
                                                    (debug_flags & 1) ? X : nullptr, nxt.hi, nxt.lo, ch, last ? 0.01f : 0.1f,
                                                    last ? 1 : 0, rm, fl, fo);
       CK(cudaGetLastError());
@@ -2371,6 +2372,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
     if (const char* e = getenv("VTTS_TC_PERSIST")) h->tc_persist = atoi(e);                 // 0: one tile per CTA also on machine-filling launches
+    if (const char* e = getenv("VTTS_TC_DBGSKIP")) h->tc_dbgskip = atoi(e);                 // timing experiments only (wrong results)
     if (const char* e = getenv("VTTS_TC_COAL")) h->tc_coal = atoi(e);                       // 1: coalesced (transposed) epilogue on launches without split-K
     if (const char* e = getenv("VTTS_TC_PERSIST_MIN")) h->tc_persist_min = std::max(1, atoi(e));   // tiles per SM from which the persistent grid is used
     if (const char* e = getenv("VTTS_MRF_BRANCH")) h->mrf_branch = atoi(e);
@@ -2720,7 +2722,7 @@ int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host
       h->begin_planes();
       pq = h->planes(58, T, 1, 3 * H);
       h->flush_tails(dl, dl + 1);
-      h->klaunch(split_planes_kernel, dim3(T, 1), dim3(64), (size_t)0, (const float*)dq, 3 * H, pq.hi, pq.lo, 3 * H, 3 * H, 1.f, 0, 1, (const int*)dl, (const int*)(dl + 1));
+      h->klaunch(split_planes_kernel, dim3((T + EW_ROWS - 1) / EW_ROWS, 1), dim3(EW_THREADS), (size_t)0, (const float*)dq, 3 * H, pq.hi, pq.lo, 3 * H, 3 * H, 1.f, 0, 1, (const int*)dl, (const int*)(dl + 1));
     }
     auto once = [&] {
       if (use_tc) h->launch_attn_tc(pq, dout, nullptr, *L, H, dl, dl + 1, T);
