@@ -333,6 +333,68 @@ def extras(cfg, blob, manifest, eng, dev, pk):
     return out
 
 
+def sharded_batch(cfg, eng, dev, rank, world, steps=16):
+    """BASELINE configs[3]: 64 utterances per GPU (64-256 phonemes), one global list sharded over the ranks by
+    parallel.lpt_shards, every rank synthesises its shard in one batched call per step; no collective on the data path.
+    Timed with CUDA events on the engine stream, max over ranks.  Every rank reaches the two collectives at the end
+    whatever happened before them (a failure on one rank is reported, not waited for)."""
+    import torch
+    import torch.distributed as dist
+    from vosk_tts_b200 import parallel
+    err, mine_ms, n, B = None, 0.0, 0.0, 0
+    n_all = 64 * world
+    try:
+        g = torch.Generator().manual_seed(3)
+        lens_all = torch.randint(64, 257, (n_all,), generator=g).numpy().astype(np.int64)
+        ids_all = torch.randint(0, cfg["n_vocab"], (n_all, 256), generator=g).numpy().astype(np.int64)
+        sid_all = torch.randint(0, 5, (n_all,), generator=g).numpy().astype(np.int64)
+        mine = parallel.lpt_shards(lens_all, world)[rank]
+        lens, sid = lens_all[mine], sid_all[mine]
+        ids = np.ascontiguousarray(ids_all[mine][:, : int(lens.max())])
+        B = len(mine)
+        d_ids, d_sid = torch.as_tensor(ids, device=dev), torch.as_tensor(sid, device=dev)
+        scales = np.array([0.8, 1.0, 0.8], np.float32)
+        yl = eng.durations_dev(d_ids.data_ptr(), lens, d_sid.data_ptr(), B, ids.shape[1], scales, 0, seed=11)
+        maxf = int(yl.max())
+        d_wav = torch.zeros(B, maxf * eng.hop, device=dev)
+        eng.synthesize_dev(d_wav.data_ptr(), maxf * eng.hop)
+        est = torch.cuda.ExternalStream(eng.stream(), device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def step():
+            return eng.infer_dev(d_ids.data_ptr(), lens, d_sid.data_ptr(), B, ids.shape[1], scales, d_wav.data_ptr(), maxf * eng.hop, seed=11)
+        for _ in range(3):
+            yl = step()
+        ms = []
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(est)
+            yl = step()
+            e1.record(est)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        torch.cuda.synchronize()
+        mine_ms = float(sum(ms))
+        n = float(int(yl.sum()) * eng.hop * steps)
+        del d_wav, flush
+    except Exception as ex:      # noqa: BLE001
+        err = repr(ex)
+    t = torch.tensor([mine_ms, -mine_ms if err is None else -1e30, 1.0 if err else 0.0], device=dev, dtype=torch.float64)
+    tn = torch.tensor([n], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+    worst, best, failed = float(t[0]), -float(t[1]), float(t[2]) > 0
+    if failed or worst <= 0:
+        return {"error": err or "another rank failed"}
+    return {"workload": "BASELINE configs[3]: %d utterances (64-256 phonemes, seed 3) sharded %d ways by parallel.lpt_shards, one batched call per "
+                        "rank and step, weights from the one NCCL broadcast, no data-path collective" % (n_all, world),
+            "steps": steps, "utterances_rank0": B, "value": float(tn[0]) / (worst / 1e3), "unit": "samples/s",
+            "ms_per_step_slowest_rank": worst / steps, "ms_per_step_fastest_rank": best / steps, "timed_region_s": worst / 1e3}
+
+
 def main():
     if len(sys.argv) >= 4 and sys.argv[1] == "--cpu-worker":
         cpu_worker_main(int(sys.argv[2]), int(sys.argv[3]))
@@ -520,6 +582,9 @@ def main():
     r2 = eng.graph_replays()
     h2, m2 = eng.speculation_stats()
     barrier()
+    sharded = None
+    if world > 1 and not args.no_extras:
+        sharded = sharded_batch(cfg, eng, dev, rank, world)
     n_samples = Ty * hop
     if world > 1:
         t = torch.tensor([total_ms, e2e_total, float(sum(cold_t))], device=dev, dtype=torch.float64)
@@ -613,7 +678,8 @@ def main():
                                               "tflops": (o_fl / (o_ms / 1e3) / 1e12) if o_ms > 0 else 0.0,
                                               "launches_per_step": o_n / max(args.steps, 1)},
                              "profiled_ms_per_step": prof_total_ms / max(args.steps, 1)},
-                "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage, "extra": extra,
+                "cpu_baseline": cpu, "clocks": clocks, "stage_ms": stage,
+                "extra": extra if sharded is None else dict(extra or {}, configs3_sharded=sharded),
                 "init": {"seconds": init_s, "weight_broadcast_ms": bcast_ms, "weight_bytes": 4 * nblob,
                          "graph_replays": eng.graph_replays()}}
         print(json.dumps(line))

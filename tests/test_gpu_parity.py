@@ -390,12 +390,16 @@ def test_bucketed_graphs_serve_unseen_utterances(engine, cfg):
 @pytest.mark.parametrize("env", [{"VTTS_TC_BN": "128"}, {"VTTS_TC_TALL": "1"}, {"VTTS_PDL": "0"}, {"VTTS_CONV_MAXS": "1", "VTTS_CONV_MAXG": "4"},
                                  {"VTTS_ATTN_ROWS": "4"}, {"VTTS_TC_MULTICAST": "1"}, {"VTTS_TC_SPLIT": "1"}, {"VTTS_TC_SPLIT": "2"},
                                  {"VTTS_TC_MINSTEPS": "1"}, {"VTTS_TC_BN": "128", "VTTS_TC_MINSTEPS": "1"}, {"VTTS_TC_BN": "64"}, {"VTTS_ATTN_SPLIT": "0"},
-                                 {"VTTS_CONV_AUTOG": "0"}, {"VTTS_MRF_BRANCH": "1"}, {"VTTS_BUCKETS": "0"}, {"VTTS_ATTN_TC": "0"}],
+                                 {"VTTS_CONV_AUTOG": "0"}, {"VTTS_MRF_BRANCH": "1"}, {"VTTS_BUCKETS": "0"}, {"VTTS_ATTN_TC": "0"},
+                                 {"VTTS_TC_PERSIST": "2", "VTTS_TC_SPLIT": "1"}, {"VTTS_TC_PERSIST": "2", "VTTS_TC_SPLIT": "1", "VTTS_TC_TALL": "-1"},
+                                 {"VTTS_TC_PERSIST": "2", "VTTS_TC_SPLIT": "1", "VTTS_TC_WMC": "1"},
+                                 {"VTTS_TC_PERSIST": "2", "VTTS_TC_SPLIT": "1", "VTTS_TC_COAL": "1", "VTTS_TC_BN": "128"}, {"VTTS_TC_SPLIT": "1", "VTTS_TC_COAL": "1"}],
                          ids=["tc-128-wide-tiles", "tc-tall-activation-tiles", "no-programmatic-dependent-launch", "ffma-no-cluster-4-groups",
                               "attention-4-rows-per-warp", "tc-tma-multicast-cluster", "tc-no-split-k", "tc-split-k-pairs",
                               "tc-split-k-8-ways", "tc-128-wide-split-k-8-ways", "tc-64-wide-only", "attention-without-split-kv",
                               "ffma-single-thread-group", "mrf-chains-on-separate-streams", "exact-sizes-no-length-buckets",
-                              "ffma-attention-in-the-flow"])
+                              "ffma-attention-in-the-flow", "tc-persistent-tile-loop-tall", "tc-persistent-tile-loop-per-tap-tiles",
+                              "tc-persistent-weight-multicast-pairs", "tc-persistent-coalesced-epilogue-128-wide", "tc-coalesced-epilogue"])
 def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
     """The tuning switches select different tilings / launch modes of the same kernels (128-wide tcgen05 tiles are what
     batched calls use automatically); each must still reproduce the reference fixture."""

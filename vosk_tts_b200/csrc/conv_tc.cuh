@@ -76,6 +76,8 @@ struct TcBatch {
   int ast, wst; // ring depths (activation / weight tiles) for this launch
   int dbgskip;  // tuning experiments (timing only, wrong results): 1 = no epilogue stores, 2 = no MMAs issued, 4 = no residual loads
   int coal;     // 1: launches without split-K finish their tiles through the shared-memory transposition (coalesced rows)
+  int wmc;      // persistent launches: 2 = CTA pairs (cluster (2,1,1)) walk adjacent row tiles and share every weight tile: each CTA
+                //   fetches half of it and TMA-multicasts it into both (halves the L2 reads of the dominant operand); 1 = off
   int persist;  // 1: 1-D grid of resident CTAs walking the (gx, gy, gz) tile space (machine-filling launches)
   int gx, gy, gz;
   int split;    // cluster split-K: `split` CTAs (cluster dims (1,1,split)) each run a contiguous range of the k-steps of one
@@ -440,6 +442,7 @@ constexpr int TC_MAXST = 4;   // barrier slots per ring
 struct TcTile {
   const TcProblem* P;
   int b, co0, t0, sp;
+  int t0u;          // first row of the scheduling unit (== t0, or the pair's first tile with weight multicast)
   bool valid;       // the problem has this channel tile (grouped problems may differ in Cout)
 };
 
@@ -462,20 +465,27 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const bool persist = !SPLIT && tb.persist != 0;
   const int A_BYTES = tb.a_bytes;
   const bool tall = tb.tall != 0;
-  const int ntiles = persist ? tb.gx * tb.gy * tb.gz : 1;
-  const int tstride = persist ? (int)gridDim.x : 1;
-  const int tile0 = persist ? (int)blockIdx.x : 0;
+  const int wmc = persist ? tb.wmc : 1;                    // CTAs sharing each weight tile (scheduling unit = wmc adjacent row tiles)
+  const uint32_t wrank = wmc > 1 ? cluster_rank() : 0u;
+  const int gxu = (tb.gx + wmc - 1) / wmc;
+  const int ntiles = persist ? gxu * tb.gy * tb.gz : 1;
+  const int tstride = persist ? (int)gridDim.x / wmc : 1;
+  const int tile0 = persist ? (int)blockIdx.x / wmc : 0;
   auto decode = [&](int tile) {
     int bx, by, bz;
+    int bxu;
     if (persist) {
-      bx = tile % tb.gx;
-      const int r = tile / tb.gx;
+      bxu = tile % gxu;
+      const int r = tile / gxu;
       by = r % tb.gy;
       bz = r / tb.gy;
+      bx = bxu * wmc + (int)wrank;
     } else {
       bx = blockIdx.x; by = blockIdx.y; bz = blockIdx.z;
+      bxu = bx;
     }
     TcTile t;
+    t.t0u = bxu * wmc * TC_BM;
     const int zi = bz / S;
     t.sp = bz - zi * S;
     t.P = &tb.p[zi % tb.n];
@@ -505,7 +515,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], (uint32_t)tb.cn); }
-    for (int s = 0; s < TC_WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < TC_WST; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], (uint32_t)wmc); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int q = 0; q < (persist ? tb.n : 1); ++q) {
@@ -531,7 +541,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const int cn = tb.cn;
   const uint32_t crank = cn > 1 ? cluster_rank() : 0u;
   const uint16_t cmask = (uint16_t)((1u << cn) - 1u);
-  if (cn > 1) cluster_sync_all();        // every peer's mbarriers exist before anybody multicasts into / arrives on them
+  if (cn > 1 || wmc > 1) cluster_sync_all();   // every peer's mbarriers exist before anybody multicasts into / arrives on them
   // Weights are immutable: the first ring of weight tiles is requested before waiting for the producer of the activations.
   // (lens/offs are final before any graph that reads them starts -- host copies or the previous phase's graph -- so the
   //  peek below only decides whether prefetching is worth it: idle CTAs of ragged batches must not fetch and then drain
@@ -540,6 +550,14 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   auto issue_w = [&](const TcProblem& P, int co0, int c, int j, int wst) {
     uint8_t* wb = smem_w + wst * NP * B_BYTES;
     mbar_expect_tx(&w_full[wst], NP * B_BYTES);
+    if (wmc > 1) {
+      // this CTA fetches channel rows [wrank, wrank + 1) * BN/2 of the tile and multicasts them into both CTAs of the pair;
+      // the other half arrives from the peer and signals the same barrier
+      const int half = (int)wrank * (BN / 2);
+      tma_load_2d_mc(wb + half * 128, &P.w_hi, c * TC_BK, j * P.Cout + co0 + half, &w_full[wst], (uint16_t)3);
+      tma_load_2d_mc(wb + B_BYTES + half * 128, &P.w_lo, c * TC_BK, j * P.Cout + co0 + half, &w_full[wst], (uint16_t)3);
+      return;
+    }
     tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
@@ -574,7 +592,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         if (!T.valid) continue;
         const TcProblem& P = *T.P;
         const int L = lens[T.b] * tb.rmul + P.in_extra;
-        if (T.t0 >= L) {
+        if (T.t0u >= L) {
           // nothing to compute; prefetched weight tiles must have landed before this CTA's shared memory is released
           for (int i = 0; i < w_pre; ++i) mbar_wait(&w_full[i], 0);
           continue;
@@ -631,7 +649,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
         if (!T.valid) continue;
         const TcProblem& P = *T.P;
         const int L = lens[T.b] * tb.rmul + P.in_extra;
-        if (T.t0 >= L) continue;
+        if (T.t0u >= L) continue;
         any_active = true;
         const int nsteps_all = (P.Cin / TC_BK) * P.k;
         const int s_beg = (int)((long)nsteps_all * T.sp / S), s_end = (int)((long)nsteps_all * (T.sp + 1) / S);
@@ -677,7 +695,8 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
               umma_bf16(tmem_acc, ahi + adv, bhi + adv, idesc, 1u);
             }
           }
-          umma_commit(&w_empty[wst]);                            // frees the weight stage when these MMAs retire
+          if (wmc > 1) umma_commit_mc(&w_empty[wst], (uint16_t)3);   // frees the weight stage (in both CTAs of a pair) when these MMAs retire
+          else umma_commit(&w_empty[wst]);
           if (++wst == TC_WST) { wst = 0; ++w_use; }
           if (++a_cnt == a_per) {                                // ... and the activation tile after its last tap
             if (cn > 1) umma_commit_mc(&a_empty[ast], cmask);    //     (in every CTA that multicasts into it)
@@ -705,7 +724,8 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
       if (!T.valid) continue;
       const TcProblem& P = *T.P;
       const int L = lens[T.b] * tb.rmul + P.in_extra;
-      if (T.t0 >= L) continue;
+      if (T.t0u >= L) continue;                              // (with weight multicast a CTA whose own tile lies behind the end of the
+                                                             //  utterance still runs the mainloop and this handshake; it stores nothing)
       const int b = T.b, co0 = T.co0, sp = T.sp;
       const int buf = lt & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(buf * BN);
@@ -804,7 +824,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   if (threadIdx.x == 64) TC_STAMP(7);
   tc_fence_before();
   __syncthreads();
-  if (cn > 1) cluster_sync_all();        // no peer may still multicast into, or arrive on, this CTA's shared memory
+  if (cn > 1 || wmc > 1) cluster_sync_all();   // no peer may still multicast into, or arrive on, this CTA's shared memory
   if (threadIdx.x == 0) TC_STAMP(8);
   if (warp == 1) {
     tc_fence_after();

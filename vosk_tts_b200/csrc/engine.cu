@@ -305,7 +305,7 @@ struct vtts_engine {
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0, tc_wmc = 0;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
@@ -805,7 +805,7 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     if (q.w.mid && q.in.mid) np3 = true;
     grid_tiles += (long)((maxLen * rmul + q.in_extra + TC_BM - 1) / TC_BM) * ((q.Cout + BN - 1) / BN) * nB;
   }
-  const bool big = tc_persist && grid_tiles > (long)tc_persist_min * n_sm;
+  const bool big = tc_persist == 2 || (tc_persist && grid_tiles > (long)tc_persist_min * n_sm);   // (2: forced, for tests)
   bool tall = tc_tall > 0 || (tc_tall == 0 && big);
   for (const TcSpec& q : ps) {
     const int nr = TC_BM + (q.k - 1) * q.dil;
@@ -881,6 +881,8 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.split = split;
   tb.cn = cn;
   tb.tall = tall ? 1 : 0;
+  // persistent launches: CTA pairs share every weight tile through TMA multicast (conv_tc.cuh)
+  const int wmc = (big && tc_wmc && split == 1 && cn == 1 && np == 2 && n_sm % 2 == 0) ? 2 : 1;
   tb.baseoff = tc_baseoff;
   tb.dbgskip = tc_dbgskip;
   tb.a_bytes = (maxNR * 128 + 1023) / 1024 * 1024;
@@ -890,8 +892,8 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     const int box_rows = tall ? TC_BM + (q.k - 1) * q.dil : TC_BM / cn;
     P.a_hi = make_map(q.in.hi, q.in.C, q.in.rows, box_rows);
     P.a_lo = make_map(q.in.lo, q.in.C, q.in.rows, box_rows);
-    P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN);
-    P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN);
+    P.w_hi = make_map(q.w.hi, q.Cin, (long)q.k * q.Cout, BN / wmc);
+    P.w_lo = make_map(q.w.lo, q.Cin, (long)q.k * q.Cout, BN / wmc);
     if (np == 3) {
       P.a_mid = make_map(q.in.mid, q.in.C, q.in.rows, box_rows);
       P.w_mid = make_map(q.w.mid, q.Cin, (long)q.k * q.Cout, BN);
@@ -918,10 +920,14 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   // machine-filling launches: one resident CTA per SM walks the tile space (conv_tc.cuh)
   tb.gx = (int)grid.x; tb.gy = (int)grid.y; tb.gz = (int)grid.z;
   tb.persist = 0;
-  if (tc_persist && split == 1 && cn == 1 && !tb.wpre && (long)grid.x * grid.y * grid.z > (long)tc_persist_min * n_sm) {
+  tb.wmc = 1;
+  if (tc_persist == 2 && split == 1 && cn == 1) tb.wpre = 0;
+  if (split == 1 && cn == 1 && !tb.wpre && (tc_persist == 2 || (tc_persist && (long)grid.x * grid.y * grid.z > (long)tc_persist_min * n_sm))) {
     tb.persist = 1;
+    tb.wmc = wmc;
     grid = dim3((unsigned)n_sm, 1, 1);
   }
+  REQUIRE(tb.persist || wmc == 1, VTTS_ERR_INVALID, "tensor-core conv: weight multicast planned for a launch that is not persistent");
   if (profiling) {
     if (tc_prof_used + 2 > tc_prof_ev.size()) {
       tc_prof_ev.resize(tc_prof_used + 2);
@@ -942,9 +948,9 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     REQUIRE(lc.dynamicSmemBytes <= 227 * 1024, VTTS_ERR_INVALID, "tensor-core conv: shared-memory budget exceeded");
     cudaLaunchAttribute at[2];
     int na = 0;
-    if (cn > 1 || split > 1) {
+    if (cn > 1 || split > 1 || tb.wmc > 1) {
       at[na].id = cudaLaunchAttributeClusterDimension;
-      at[na].val.clusterDim.x = 1; at[na].val.clusterDim.y = cn; at[na].val.clusterDim.z = split;
+      at[na].val.clusterDim.x = tb.wmc; at[na].val.clusterDim.y = cn; at[na].val.clusterDim.z = split;
       ++na;
     }
     if (use_pdl) {
@@ -2371,8 +2377,9 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_TC_MULTICAST")) h->tc_mc = atoi(e);
     if (const char* e = getenv("VTTS_TC_SPLIT")) h->tc_split = atoi(e);
     if (const char* e = getenv("VTTS_TC_MINSTEPS")) h->tc_min_steps = std::max(1, atoi(e));   // k-steps per CTA below which split-K stops
-    if (const char* e = getenv("VTTS_TC_PERSIST")) h->tc_persist = atoi(e);                 // 0: one tile per CTA also on machine-filling launches
+    if (const char* e = getenv("VTTS_TC_PERSIST")) h->tc_persist = atoi(e);                 // 0: one tile per CTA also on machine-filling launches; 2: persistent grid on every launch without split-K (tests)
     if (const char* e = getenv("VTTS_TC_DBGSKIP")) h->tc_dbgskip = atoi(e);                 // timing experiments only (wrong results)
+    if (const char* e = getenv("VTTS_TC_WMC")) h->tc_wmc = atoi(e);                         // 1: weight-tile multicast between CTA pairs of persistent launches (measured neutral, off)
     if (const char* e = getenv("VTTS_TC_COAL")) h->tc_coal = atoi(e);                       // 1: coalesced (transposed) epilogue on launches without split-K
     if (const char* e = getenv("VTTS_TC_PERSIST_MIN")) h->tc_persist_min = std::max(1, atoi(e));   // tiles per SM from which the persistent grid is used
     if (const char* e = getenv("VTTS_MRF_BRANCH")) h->mrf_branch = atoi(e);
