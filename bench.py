@@ -560,14 +560,23 @@ def main():
         return {"input": torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy().astype(np.int64), "input_lengths": np.array([T], np.int64),
                 "scales": wl["scales"], "sid": np.array([int(torch.randint(0, 200, (1,), generator=g))], np.int64), "bert": None,
                 "phone_duration_extra": None}
+    # what a service does at start-up: size the workspace for the largest request it will take (here: <= 128 phonemes, <= 768
+    # frames), so that no later call moves a buffer and invalidates the length buckets' CUDA graphs
+    reserved_frames = sess.reserve(128, 768)
     r0 = eng.graph_replays()
     first_seen = []
     N_COLD_WARM, N_COLD = 150, 40
+    def frame_bucket(n):         # engine.cu::bucket_frm
+        return (n + 31) // 32 * 32 if n <= 256 else ((n + 63) // 64 * 64 if n <= 1024 else (n + 127) // 128 * 128)
+    seen_buckets = set()
     for i in range(N_COLD_WARM):
         f = fresh()
         t1 = time.perf_counter()
         sess.run(None, f)
         first_seen.append(time.perf_counter() - t1)
+        seen_buckets.add(((int(f["input_lengths"][0]) + 15) // 16 * 16, frame_bucket(int(sess.last_y_lengths[0]))))
+    n_warm_buckets = len(seen_buckets)
+    new_in_timed = []
     cold_t, cold_n = [], 0
     r1 = eng.graph_replays()
     h1, m1 = eng.speculation_stats()
@@ -579,6 +588,10 @@ def main():
         a = sess.run(None, f)[0]
         cold_t.append(time.perf_counter() - t1)
         cold_n += int(sess.last_wav_lengths[0])
+        key = ((int(f["input_lengths"][0]) + 15) // 16 * 16, frame_bucket(int(sess.last_y_lengths[0])))
+        if key not in seen_buckets:
+            seen_buckets.add(key)
+            new_in_timed.append([key[0], key[1], round(1e3 * cold_t[-1], 2)])
     r2 = eng.graph_replays()
     h2, m2 = eng.speculation_stats()
     barrier()
@@ -661,6 +674,8 @@ def main():
                              "phonemes": "100..128 (uniform), random speaker, engine-drawn noise",
                              "graph_replays_in_timed_region": r2 - r1, "graph_launches_expected": 2 * N_COLD,
                              "speculation_hits_misses": [h2 - h1, m2 - m1],
+                             "length_buckets_seen_in_warmup": n_warm_buckets, "first_seen_buckets_in_timed_region_tokens_frames_ms": new_in_timed,
+                             "workspace_reserved": "Engine.reserve(128 phonemes, 768 frames) before the warm-up (reached %d frames): no buffer moves afterwards" % reserved_frames,
                              "warmup": "150 OTHER distinct utterances of the same distribution (rank 0: %d graph replays among them); a length "
                                        "bucket's first call runs eagerly and captures its graph (calls 1-3 of a fresh engine: %.2f / %.2f / %.2f ms, "
                                        "incl. lazy kernel loading); such calls inside the timed region are what separates the mean from the median"

@@ -427,6 +427,32 @@ def test_alternative_kernel_configurations_match_golden(packed, cfg, env):
     e.close()
 
 
+def test_reserved_workspace_keeps_bucket_graphs_valid(packed, cfg):
+    """Engine.reserve sizes the workspace once; afterwards a longer request must not move buffers, i.e. the CUDA graphs captured
+    for shorter requests keep replaying (without the reservation every growth invalidates all of them)."""
+    from vosk_tts_b200.engine import Engine
+    g = torch.Generator().manual_seed(11)
+    short = torch.randint(0, cfg["n_vocab"], (1, 24), generator=g).numpy()
+    longer = torch.randint(0, cfg["n_vocab"], (1, 90), generator=g).numpy()
+    for reserve in (True, False):
+        e = Engine(cfg, packed[0], packed[1], device=0, precision=1)
+        if reserve:
+            assert e.reserve(96, 512) >= 512
+        ref = None
+        for _ in range(3):                                   # eager + capture, then replays
+            w, yl = e.infer(short, [24], [1], (0.667, 1.0, 0.8), seed=5, frames_hint=256)
+            ref = w if ref is None else ref
+            assert np.array_equal(w, ref)
+        r0 = e.graph_replays()
+        e.infer(longer, [90], [1], (0.667, 1.0, 0.8), seed=6, frames_hint=1024)      # new, larger buckets
+        r1 = e.graph_replays()
+        w, yl = e.infer(short, [24], [1], (0.667, 1.0, 0.8), seed=5, frames_hint=256)
+        assert np.array_equal(w, ref)
+        if reserve:
+            assert e.graph_replays() - r1 == 2, "the short request's two graphs were invalidated by a longer request"
+        e.close()
+
+
 def test_plain_hifigan_resblock2_variant_vs_oracle(cfg):
     """Config-driven variant: plain HiFi-GAN `Generator` tail (conv_post + tanh, speaker projection added to conv_pre,
     models.py:845-898) with ResBlock2 (modules.py:234-258), three upsampling stages 8x8x4.  The reference's own `infer`

@@ -305,7 +305,7 @@ struct vtts_engine {
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0, tc_wmc = 0;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, conv_big_g = 1, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0, tc_wmc = 0;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
@@ -1400,10 +1400,11 @@ void vtts_engine::launch_conv(const std::vector<ConvP>& ps, int rmul, const int*
   long base0 = 0;
   for (const ConvP& q : ps)
     for (int b = 0; b < nB; ++b) base0 += (long)((hl0[b] * rmul + q.in_extra + CV_TT - 1) / CV_TT) * ((q.Cout + CV_TC - 1) / CV_TC);
-  // many tiles (batched calls): 4 thread groups per CTA, no cluster.  Few tiles (batch 1): the k-steps of a tile are
+  // many tiles (batched calls): one thread group per CTA (several CTAs per SM; r2, batch 64: 6.98 ms per step against 8.01 / 8.21
+  // with 2 / 4 groups), no cluster.  Few tiles (batch 1): the k-steps of a tile are
   // spread over a cluster of S CTAs until the launch fills ~1 wave of SMs; ranks that still have long k-loops then get
   // 2-4 thread groups each (a lone warp per scheduler issues an FFMA only every other cycle).
-  int G = base0 >= 2 * 148 ? conv_max_g : conv_min_g;
+  int G = base0 >= 2 * 148 ? conv_big_g : conv_min_g;
   for (const ConvP& q : ps)
     while (G > 1 && q.Cin % (CV_CK * G) != 0) G >>= 1;
   auto min_steps = [&](int g) {
@@ -1515,9 +1516,13 @@ void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, c
     P.pw_w = d[i].pw.w; P.pw_b = d[i].pw.b; P.ldw = d[i].pw.ldw;
     P.ln2g = d[i].ln2.g; P.ln2b = d[i].ln2.b;
     P.C = C; P.k = k; P.dil = dil;
-    dim3 grid((maxLen + DDS_TT - 1) / DDS_TT, B);
-    const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * DDS_TT + 8 * DDS_TT) * sizeof(float);
-    klaunch(dds_layer_kernel, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
+    // batched calls: 16 positions per CTA (every CTA streams the whole 1x1 weight matrix); single utterances: 4 (more CTAs)
+    const bool wide = (long)maxLen * B >= 4096;
+    const int tt = wide ? DDS_TTB : DDS_TT;
+    dim3 grid((maxLen + tt - 1) / tt, B);
+    const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * tt + 8 * tt) * sizeof(float);
+    if (wide) klaunch(dds_layer_kernel<DDS_TTB>, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
+    else klaunch(dds_layer_kernel<DDS_TT>, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
     CK(cudaGetLastError());
     ++launches;
     std::swap(a, b);
@@ -2371,6 +2376,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     if (const char* e = getenv("VTTS_CONV_MAXS")) h->conv_max_s = std::max(1, atoi(e));
     if (const char* e = getenv("VTTS_CONV_TARGET")) h->conv_target = std::max(1, atoi(e));
     if (const char* e = getenv("VTTS_CONV_MAXG")) h->conv_max_g = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("VTTS_CONV_BIGG")) h->conv_big_g = std::max(1, std::min(4, atoi(e)));   // thread groups per CTA on machine-filling FFMA launches
     if (const char* e = getenv("VTTS_TC_TALL")) h->tc_tall = atoi(e);
     if (const char* e = getenv("VTTS_TC_BASEOFF")) h->tc_baseoff = atoi(e);
     if (const char* e = getenv("VTTS_TC_BN")) h->tc_bn = atoi(e);
@@ -2401,7 +2407,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->bind_weights();
     h->build_prefetch_list();
     CK(cudaMemsetAsync(h->ensure(h->d_done_ctr, 4), 0, 4 * sizeof(int), h->stream));     // ticket counter of duration_kernel (self-resetting)
-    CK(cudaFuncSetAttribute(dds_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(dds_layer_kernel<DDS_TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CK(cudaFuncSetAttribute(dds_layer_kernel<DDS_TTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<128>()));

@@ -1015,7 +1015,8 @@ attn_split_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out
 // One DDSConv layer (modules.py:96-108): depthwise dilated conv k -> LN -> GELU(erf) -> 1x1 -> LN ->
 // GELU -> + x.  One CTA = 8 positions x all C channels (C == blockDim.x <= 256).
 // ------------------------------------------------------------------------------------------------
-constexpr int DDS_TT = 4;      // positions per CTA
+constexpr int DDS_TT = 4;      // positions per CTA (single utterances)
+constexpr int DDS_TTB = 16;    // ... batched calls
 constexpr int DDS_CH = 32;     // 1x1 weight rows (input channels) per cp.async chunk
 constexpr int DDS_NS = 4;      // chunk ring depth
 
@@ -1034,12 +1035,12 @@ struct DdsP {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
-__device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, int C, float (&mean)[DDS_TT],
-                                               float (&rstd)[DDS_TT]) {
+template <int TT>
+__device__ __forceinline__ void block_ln_stats(float (&v)[TT], float* red, int C, float (&mean)[TT], float (&rstd)[TT]) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  float s[DDS_TT];
+  float s[TT];
 #pragma unroll
-  for (int i = 0; i < DDS_TT; ++i) {
+  for (int i = 0; i < TT; ++i) {
     s[i] = v[i];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
@@ -1047,16 +1048,16 @@ __device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, i
   __syncthreads();
   if (lane == 0)
 #pragma unroll
-    for (int i = 0; i < DDS_TT; ++i) red[warp * DDS_TT + i] = s[i];
+    for (int i = 0; i < TT; ++i) red[warp * TT + i] = s[i];
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < DDS_TT; ++i) {
+  for (int i = 0; i < TT; ++i) {
     float t = 0.f;
-    for (int w = 0; w < nw; ++w) t += red[w * DDS_TT + i];
+    for (int w = 0; w < nw; ++w) t += red[w * TT + i];
     mean[i] = t / (float)C;
   }
 #pragma unroll
-  for (int i = 0; i < DDS_TT; ++i) {
+  for (int i = 0; i < TT; ++i) {
     const float d = v[i] - mean[i];
     s[i] = d * d;
 #pragma unroll
@@ -1065,18 +1066,21 @@ __device__ __forceinline__ void block_ln_stats(float (&v)[DDS_TT], float* red, i
   __syncthreads();
   if (lane == 0)
 #pragma unroll
-    for (int i = 0; i < DDS_TT; ++i) red[warp * DDS_TT + i] = s[i];
+    for (int i = 0; i < TT; ++i) red[warp * TT + i] = s[i];
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < DDS_TT; ++i) {
+  for (int i = 0; i < TT; ++i) {
     float t = 0.f;
-    for (int w = 0; w < nw; ++w) t += red[w * DDS_TT + i];
+    for (int w = 0; w < nw; ++w) t += red[w * TT + i];
     rstd[i] = rsqrtf(t / (float)C + 1e-5f);
   }
 }
 
-// One CTA = DDS_TT positions x all C channels (thread c owns channel c).  The 1x1 weight matrix streams through a
+// One CTA = TT positions x all C channels (TT = TT for single utterances: more CTAs; TTB for batches: every CTA streams
+// the whole 1x1 weight matrix, so more positions per CTA means less L2 traffic and more FFMAs per shared-memory read;
+// the arithmetic per position is the same in both) (thread c owns channel c).  The 1x1 weight matrix streams through a
 // 3-deep cp.async ring of 32-row chunks; the first chunks are in flight while the depthwise conv and LN run.
+template <int TT>
 __global__ void __launch_bounds__(256)
 dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restrict__ offs) {
   PDL_LAUNCH();
@@ -1084,14 +1088,14 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
   // they (and the immutable weights) may be touched before PDL_WAIT
   const int b = blockIdx.y;
   const int len = lens[b];
-  const int t0 = blockIdx.x * DDS_TT;
+  const int t0 = blockIdx.x * TT;
   if (t0 >= len) return;
   const long base = offs[b];
   const int C = P.C, c = threadIdx.x;
   extern __shared__ __align__(16) float dsm[];
   float* Wr = dsm;                                   // [NS][CH][C]
   float* ys = Wr + DDS_NS * DDS_CH * C;              // [C][TT]
-  float* red = ys + C * DDS_TT;                      // [8][TT]
+  float* red = ys + C * TT;                      // [8][TT]
   const int nch = C / DDS_CH;
   __shared__ uint64_t wfull[DDS_NS];
   if (c == 0) {
@@ -1113,7 +1117,7 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
     if (i < nch) issue_chunk(i);
   PDL_WAIT();                                        // P.x comes from the previous kernel
 
-  float v[DDS_TT], mean[DDS_TT], rstd[DDS_TT];
+  float v[TT], mean[TT], rstd[TT];
   const int half = (P.k - 1) / 2;
   const float fpw = P.x0 ? P.pre_w[c] : 0.f, fpb = P.x0 ? P.pre_b[c] : 0.f;
   auto ld_x = [&](int t) -> float {
@@ -1122,7 +1126,7 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
     return P.x[row * (long)C + c];
   };
 #pragma unroll
-  for (int i = 0; i < DDS_TT; ++i) {
+  for (int i = 0; i < TT; ++i) {
     float a = P.sep_b[c];
     for (int j = 0; j < P.k; ++j) {
       const int t = t0 + i + (j - half) * P.dil;
@@ -1131,42 +1135,48 @@ dds_layer_kernel(const DdsP P, const int* __restrict__ lens, const int* __restri
     v[i] = a;
   }
   timeline_stamp(-1);
-  block_ln_stats(v, red, C, mean, rstd);
+  block_ln_stats<TT>(v, red, C, mean, rstd);
   timeline_stamp(-2);
   {
     const float g = P.ln1g[c], be = P.ln1b[c];
-    float4 o;
-    o.x = gelu_erf((v[0] - mean[0]) * rstd[0] * g + be);
-    o.y = gelu_erf((v[1] - mean[1]) * rstd[1] * g + be);
-    o.z = gelu_erf((v[2] - mean[2]) * rstd[2] * g + be);
-    o.w = gelu_erf((v[3] - mean[3]) * rstd[3] * g + be);
-    *reinterpret_cast<float4*>(ys + c * DDS_TT) = o;
+#pragma unroll
+    for (int i = 0; i < TT; i += 4) {
+      float4 o;
+      o.x = gelu_erf((v[i] - mean[i]) * rstd[i] * g + be);
+      o.y = gelu_erf((v[i + 1] - mean[i + 1]) * rstd[i + 1] * g + be);
+      o.z = gelu_erf((v[i + 2] - mean[i + 2]) * rstd[i + 2] * g + be);
+      o.w = gelu_erf((v[i + 3] - mean[i + 3]) * rstd[i + 3] * g + be);
+      *reinterpret_cast<float4*>(ys + c * TT + i) = o;
+    }
   }
   {
     const float bias = P.pw_b[c];
 #pragma unroll
-    for (int i = 0; i < DDS_TT; ++i) v[i] = bias;
+    for (int i = 0; i < TT; ++i) v[i] = bias;
   }
   for (int ch = 0; ch < nch; ++ch) {
     __syncthreads();                                 // ys visible (first iteration); slot (ch-1)%NS has been consumed
     if (ch + DDS_NS - 1 < nch) issue_chunk(ch + DDS_NS - 1);
     mbar_wait(&wfull[ch % DDS_NS], (ch / DDS_NS) & 1);   // chunk ch landed
     const float* wr = Wr + (ch % DDS_NS) * DDS_CH * C + c;
-    const float* yy = ys + ch * DDS_CH * DDS_TT;
+    const float* yy = ys + ch * DDS_CH * TT;
 #pragma unroll 8
     for (int ci = 0; ci < DDS_CH; ++ci) {
       const float w = wr[ci * C];
-      const float4 y0 = *reinterpret_cast<const float4*>(yy + ci * DDS_TT);
-      v[0] = fmaf(w, y0.x, v[0]); v[1] = fmaf(w, y0.y, v[1]); v[2] = fmaf(w, y0.z, v[2]); v[3] = fmaf(w, y0.w, v[3]);
+#pragma unroll
+      for (int i = 0; i < TT; i += 4) {
+        const float4 y0 = *reinterpret_cast<const float4*>(yy + ci * TT + i);
+        v[i] = fmaf(w, y0.x, v[i]); v[i + 1] = fmaf(w, y0.y, v[i + 1]); v[i + 2] = fmaf(w, y0.z, v[i + 2]); v[i + 3] = fmaf(w, y0.w, v[i + 3]);
+      }
     }
   }
   timeline_stamp(-3);
-  block_ln_stats(v, red, C, mean, rstd);
+  block_ln_stats<TT>(v, red, C, mean, rstd);
   timeline_stamp(-4);
   {
     const float g = P.ln2g[c], be = P.ln2b[c];
 #pragma unroll
-    for (int i = 0; i < DDS_TT; ++i) {
+    for (int i = 0; i < TT; ++i) {
       const int t = t0 + i;
       if (t < len) {
         const long idx = (base + t) * (long)C + c;

@@ -313,6 +313,29 @@ class Engine:
         self._B = B
         return y_len
 
+    def reserve(self, max_tokens=256, max_frames=1024, batch=1):
+        """Sizes the engine's workspace (device buffers, plane pools, pinned staging) once for calls of up to `batch`
+        utterances x `max_tokens` phonemes x `max_frames` frames, by synthesising one synthetic request of that size.
+        Any LATER growth of the workspace moves buffers and therefore invalidates every captured CUDA graph (each length
+        bucket then pays its capture again, ~15 ms); a service calls this once at start-up, like the reference server
+        warms its ONNX session.  Returns the frame count that was reached."""
+        T, B = int(max_tokens), int(batch)
+        nv = int(self.cfg["n_vocab"])
+        ids = (np.arange(B * T, dtype=np.int64).reshape(B, T) * 7 + 1) % nv
+        lens, sid = [T] * B, [0] * B
+        e1 = np.zeros((B, 2, T), np.float32)
+        ls, F, yl = 1.0, 0, None
+        for _ in range(5):
+            yl = self.durations(ids, lens, sid, (0.667, ls, 0.8), e1)
+            F = int(yl.max())
+            if F >= max_frames:
+                break
+            ls *= max_frames / max(F, 1) * 1.05
+        ez = np.zeros((B, int(self.cfg["inter_channels"]), F), np.float32)
+        self.synthesize(yl, ez)
+        self.infer(ids, lens, sid, (0.667, ls, 0.8), None, None, seed=1, frames_hint=F + 64)
+        return F
+
     # ---- streaming (one utterance): flow once, then vocode chunk by chunk
     def synthesize_stream(self, ids, sid, scales, chunk_frames=64, noise_dp=None, noise_z=None, seed=0):
         """Generator of float32 chunks; concatenated they equal `infer(...)` of the same inputs."""

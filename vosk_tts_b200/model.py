@@ -45,6 +45,15 @@ def load_dictionary(path):
     return dic
 
 
+def _reserve_from_env():
+    """VTTS_RESERVE="tokens,frames[,batch]" (default "256,1024"; "0" = off): workspace reservation at load time, so that the
+    first long sentence does not move buffers and invalidate the CUDA graphs captured for the short ones."""
+    v = os.environ.get("VTTS_RESERVE", "256,1024")
+    if v.strip() in ("", "0"):
+        return None
+    return tuple(int(x) for x in v.split(","))
+
+
 class Model:
     def __init__(self, model_path=None, model_name=None, lang=None, device=0, precision=1, session=None):
         if model_path is None:
@@ -69,7 +78,7 @@ class Model:
             sr = int(self.config.get("audio", {}).get("sample_rate", 22050))
             cfg = _onnx.config_from_onnx(str(model_path / "model.onnx"), sampling_rate=sr)
             folded = _onnx.state_dict_from_onnx(str(model_path / "model.onnx"))
-            self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision)
+            self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision, reserve=_reserve_from_env())
             return
         if "model" in self.config and "data" in self.config:
             n_vocab = len(self.config.get("phoneme_id_map", {})) or 62
@@ -82,7 +91,7 @@ class Model:
         if not cks:
             raise FileNotFoundError("no weights in %s: expected model.onnx (deployed layout) or G_*.pth / model.pth" % model_path)
         folded = _weights.load_checkpoint(cks[-1])
-        self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision)
+        self.onnx = VitsSession(state_dict=folded, cfg=cfg, device=device, precision=precision, reserve=_reserve_from_env())
 
     def get_model_path(self, model_name, lang):
         for directory in MODEL_DIRS:

@@ -17,9 +17,10 @@ from .engine import Engine
 
 
 class VitsSession:
-    def __init__(self, state_dict=None, cfg=None, device=0, seed=0, packed=None, precision=0):
+    def __init__(self, state_dict=None, cfg=None, device=0, seed=0, packed=None, precision=0, reserve=None):
         """state_dict: reference checkpoint `['model']` dict (weight_g/weight_v allowed) or already folded.
-        packed: optional (blob, manifest) to skip packing (e.g. received through an NCCL broadcast)."""
+        packed: optional (blob, manifest) to skip packing (e.g. received through an NCCL broadcast).
+        reserve: optional (max_tokens, max_frames[, batch]) -- size the workspace for such requests now (Engine.reserve)."""
         self.cfg = cfg or _config.DEFAULT_CONFIG
         if precision > 0 and not _weights.tc_supported(self.cfg):
             logging.warning("model widths are not multiples of 64: the tcgen05 conv path is unavailable, using the fp32 kernels")
@@ -33,6 +34,14 @@ class VitsSession:
         self._calls = 0
         self.last_y_lengths = None
         self.last_wav_lengths = None
+        if reserve:
+            self.reserve(*reserve)
+
+    def reserve(self, max_tokens=256, max_frames=1024, batch=1):
+        """Workspace reservation (see Engine.reserve): later calls within these bounds never move a buffer, so the CUDA graphs
+        of the length buckets stay valid."""
+        with self._lock:
+            return self.engine.reserve(max_tokens, max_frames, batch)
 
     # -- onnxruntime-compatible surface ---------------------------------------------------------
     def get_providers(self):
