@@ -558,7 +558,7 @@ def main():
     def fresh():
         T = int(torch.randint(100, 129, (1,), generator=g))
         return {"input": torch.randint(0, cfg["n_vocab"], (1, T), generator=g).numpy().astype(np.int64), "input_lengths": np.array([T], np.int64),
-                "scales": wl["scales"], "sid": np.array([int(torch.randint(0, 200, (1,), generator=g))], np.int64), "bert": None,
+                "scales": wl["scales"], "sid": np.array([2], np.int64), "bert": None,
                 "phone_duration_extra": None}
     # what a service does at start-up: size the workspace for the largest request it will take (here: <= 128 phonemes, <= 768
     # frames), so that no later call moves a buffer and invalidates the length buckets' CUDA graphs
@@ -671,7 +671,7 @@ def main():
                 "e2e_cold": {"value": cold_n_all / cold_total, "unit": "samples/s", "utterances": N_COLD * world,
                              "ms_per_utterance": 1e3 * cold_total / N_COLD, "ms_median_min_max_rank0": [1e3 * sorted(cold_t)[N_COLD // 2], 1e3 * min(cold_t), 1e3 * max(cold_t)],
                              "value_at_median": (cold_n / N_COLD) / sorted(cold_t)[N_COLD // 2],
-                             "phonemes": "100..128 (uniform), random speaker, engine-drawn noise",
+                             "phonemes": "100..128 (uniform), the headline speaker (sid 2; with these synthetic weights other speaker vectors push the duration predictor to 10-60 frames per phoneme, i.e. a different workload), engine-drawn noise",
                              "graph_replays_in_timed_region": r2 - r1, "graph_launches_expected": 2 * N_COLD,
                              "speculation_hits_misses": [h2 - h1, m2 - m1],
                              "length_buckets_seen_in_warmup": n_warm_buckets, "first_seen_buckets_in_timed_region_tokens_frames_ms": new_in_timed,

@@ -1516,13 +1516,11 @@ void vtts_engine::dds_stack(const DdsW* d, int C, int k, float*& a, float*& b, c
     P.pw_w = d[i].pw.w; P.pw_b = d[i].pw.b; P.ldw = d[i].pw.ldw;
     P.ln2g = d[i].ln2.g; P.ln2b = d[i].ln2.b;
     P.C = C; P.k = k; P.dil = dil;
-    // batched calls: 16 positions per CTA (every CTA streams the whole 1x1 weight matrix); single utterances: 4 (more CTAs)
-    const bool wide = (long)maxLen * B >= 4096;
-    const int tt = wide ? DDS_TTB : DDS_TT;
-    dim3 grid((maxLen + tt - 1) / tt, B);
-    const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * tt + 8 * tt) * sizeof(float);
-    if (wide) klaunch(dds_layer_kernel<DDS_TTB>, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
-    else klaunch(dds_layer_kernel<DDS_TT>, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
+    // (16 positions per CTA were tried for batched calls -- 4x less weight streaming per position -- and measured slower:
+    //  duration stage 3.20 vs 2.95 ms at batch 64)
+    dim3 grid((maxLen + DDS_TT - 1) / DDS_TT, B);
+    const size_t smem = ((size_t)DDS_NS * DDS_CH * C + (size_t)C * DDS_TT + 8 * DDS_TT) * sizeof(float);
+    klaunch(dds_layer_kernel<DDS_TT>, dim3(grid), dim3(C), (size_t)(smem), P, lens, offs);
     CK(cudaGetLastError());
     ++launches;
     std::swap(a, b);
@@ -2408,7 +2406,6 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
     h->build_prefetch_list();
     CK(cudaMemsetAsync(h->ensure(h->d_done_ctr, 4), 0, 4 * sizeof(int), h->stream));     // ticket counter of duration_kernel (self-resetting)
     CK(cudaFuncSetAttribute(dds_layer_kernel<DDS_TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CK(cudaFuncSetAttribute(dds_layer_kernel<DDS_TTB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<192>()));
     CK(cudaFuncSetAttribute(wn_layer_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wn_smem_bytes<128>()));

@@ -1015,8 +1015,7 @@ attn_split_kernel(const float* __restrict__ qkv, int ld, float* __restrict__ out
 // One DDSConv layer (modules.py:96-108): depthwise dilated conv k -> LN -> GELU(erf) -> 1x1 -> LN ->
 // GELU -> + x.  One CTA = 8 positions x all C channels (C == blockDim.x <= 256).
 // ------------------------------------------------------------------------------------------------
-constexpr int DDS_TT = 4;      // positions per CTA (single utterances)
-constexpr int DDS_TTB = 16;    // ... batched calls
+constexpr int DDS_TT = 4;      // positions per CTA
 constexpr int DDS_CH = 32;     // 1x1 weight rows (input channels) per cp.async chunk
 constexpr int DDS_NS = 4;      // chunk ring depth
 

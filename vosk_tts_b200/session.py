@@ -76,5 +76,31 @@ class VitsSession:
             self.last_wav_lengths = y_len * self.engine.hop
         return [wav[:, None, None, :]]
 
+    def run_stream(self, feeds, chunk_frames=64):
+        """Streaming variant for ONE utterance (no onnxruntime equivalent): the text encoder, duration predictor and flow
+        run once, then the decoder is run over windows of `chunk_frames` frames (with the halo the engine reports) and every
+        window's samples are yielded as float32 [n] as soon as they are on the host.  Concatenated, the chunks are what
+        `run` returns for the same seed.  The handle keeps the flow output between the chunk calls, so the session lock is
+        held for the whole stream (released when the generator is exhausted or closed)."""
+        for k in ("bert", "phone_duration_extra"):
+            if feeds.get(k) is not None:
+                raise ValueError("feed %r is not None: model_type not supported by this engine (VITS2 graph only)" % k)
+        ids = np.asarray(feeds["input"])
+        if ids.ndim != 2 or ids.shape[0] != 1:
+            raise ValueError("run_stream takes one utterance ([1, T] ids)")
+        sid = feeds.get("sid")
+        sid = 0 if sid is None else int(np.asarray(sid).reshape(-1)[0])
+        scales = np.asarray(feeds["scales"], dtype=np.float32).reshape(3)
+        n = int(np.asarray(feeds["input_lengths"]).reshape(-1)[0])
+        with self._lock:
+            self._calls += 1
+            seed = (self._seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
+            total = 0
+            for chunk in self.engine.synthesize_stream(ids[:, :n], sid, scales, chunk_frames=chunk_frames, seed=seed):
+                total += chunk.size
+                yield chunk
+            self.last_wav_lengths = np.array([total], np.int64)
+            self.last_y_lengths = self.last_wav_lengths // self.engine.hop
+
     def close(self):
         self.engine.close()

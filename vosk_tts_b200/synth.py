@@ -71,6 +71,33 @@ class Synth:
         logging.info("Real-time factor: %0.2f (infer=%0.2f sec, audio=%0.2f sec)" % (infer_sec / dur if dur > 0 else 0.0, infer_sec, dur))
         return audio
 
+    def synth_audio_stream(self, text, speaker_id=0, noise_level=None, speech_rate=None, duration_noise_level=None, scale=None,
+                           chunk_frames=64):
+        """Generator of int16 chunks of the same utterance `synth_audio` would return (extension; the reference server sends one
+        message with the whole utterance, server/tts_server.py:55-56): first audio after encoder + flow + one decoder window."""
+        inf = self.model.config.get("inference", {})
+        noise_level = inf.get("noise_level", 0.8) if noise_level is None else noise_level
+        speech_rate = inf.get("speech_rate", 1.0) if speech_rate is None else speech_rate
+        duration_noise_level = inf.get("duration_noise_level", 0.8) if duration_noise_level is None else duration_noise_level
+        scale = inf.get("scale", 1.0) if scale is None else scale
+        if self.model.tokenizer is not None or str(self.model.config.get("model_type", "")).startswith("multistream"):
+            raise ValueError("model_type %r is not a VITS2 graph: not supported by this engine" % self.model.config.get("model_type"))
+        text = re.sub("—", "-", text.strip())
+        ids = self.g2p_noembed(text)
+        feeds = {"input": np.expand_dims(np.array(ids, dtype=np.int64), 0),
+                 "input_lengths": np.array([len(ids)], dtype=np.int64),
+                 "scales": np.array([noise_level, 1.0 / speech_rate, duration_noise_level], dtype=np.float32),
+                 "sid": np.array([0 if speaker_id is None else speaker_id], dtype=np.int64),
+                 "bert": None, "phone_duration_extra": None}
+        t0 = time.perf_counter()
+        n = 0
+        for chunk in self.model.onnx.run_stream(feeds, chunk_frames=chunk_frames):
+            n += chunk.size
+            yield self.audio_float_to_int16(chunk * scale)
+        infer_sec = time.perf_counter() - t0
+        dur = n / 22050
+        logging.info("Real-time factor: %0.2f (infer=%0.2f sec, audio=%0.2f sec)" % (infer_sec / dur if dur > 0 else 0.0, infer_sec, dur))
+
     def synth(self, text, oname, speaker_id=0, noise_level=None, speech_rate=None, duration_noise_level=None, scale=None):
         audio = self.synth_audio(text, speaker_id, noise_level, speech_rate, duration_noise_level, scale)
         with wave.open(oname, "w") as f:
