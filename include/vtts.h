@@ -172,6 +172,18 @@ int vtts_debug_read(vtts_handle h, const char* name, float* out, size_t max_floa
 int vtts_debug_attention(vtts_handle h, const char* layer, const float* qkv_host, int T, int use_tc, float* out_host, int iters,
                          float* ms_out);
 
+/* Monotonic Alignment Search on the GPU -- replaces monotonic_align.maximum_path (training/vits2/monotonic_align/__init__.py:6-22,
+ * core.pyx:7-43; called from SynthesizerTrn.forward, models.py:1658).  Handle-free (no engine state); errors of these two are
+ * read with vtts_last_error(NULL) on the calling thread.
+ * neg_cent: float32 [B][T_y][T_x] scores (frames x tokens, as the reference passes them); t_ys / t_xs: valid frames / tokens
+ * per item (the reference derives them from the mask sums), 0 <= t_x <= t_y required; path: int32 [B][T_y][T_x], 1 on the path.
+ * Host pointers; runs on `device`.  The _dev variant takes device pointers, overwrites d_value with the accumulated scores
+ * (like the reference's in-place update) and only enqueues on `stream` (a cudaStream_t, may be NULL). */
+int vtts_maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, int B, int T_y, int T_x, int32_t* path,
+                      int device);
+int vtts_maximum_path_dev(float* d_value, const int32_t* d_t_ys, const int32_t* d_t_xs, int B, int T_y, int T_x, int32_t* d_path,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

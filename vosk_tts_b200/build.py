@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvtts.so")
 SOURCES = ["engine.cu"]
-DEPS = ["engine.cu", "kernels.cuh", "conv_tc.cuh", "attn_tc.cuh", "wn_tc.cuh", os.path.join("..", "..", "include", "vtts.h")]
+DEPS = ["engine.cu", "kernels.cuh", "conv_tc.cuh", "attn_tc.cuh", "wn_tc.cuh", "mas.cuh", os.path.join("..", "..", "include", "vtts.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -24,6 +24,7 @@
 #include "../../include/vtts.h"
 #include "kernels.cuh"
 #include "conv_tc.cuh"
+#include "mas.cuh"
 #include "attn_tc.cuh"
 #include "wn_tc.cuh"
 
@@ -2468,7 +2469,52 @@ void vtts_destroy(vtts_handle h) {
   delete h;
 }
 
-const char* vtts_last_error(vtts_handle h) { return h ? h->err.c_str() : "null handle"; }
+static thread_local std::string g_free_err;      // last error of the handle-free entry points (vtts_maximum_path*), per thread
+const char* vtts_last_error(vtts_handle h) { return h ? h->err.c_str() : g_free_err.c_str(); }
+
+// Monotonic Alignment Search (mas.cuh).  No engine state is involved: the functions run on the current (or given) device.
+static int mas_launch(float* d_value, const int* d_ty, const int* d_tx, int B, int Ty, int Tx, int* d_path, cudaStream_t st) {
+  if (Tx > MAS_THREADS * MAS_MAXPT) { g_free_err = "vtts_maximum_path: T_x above " + std::to_string(MAS_THREADS * MAS_MAXPT); return VTTS_ERR_INVALID; }
+  const size_t smem = (size_t)2 * Tx * sizeof(float);
+  cudaError_t e = cudaMemsetAsync(d_path, 0, (size_t)B * Ty * Tx * sizeof(int), st);
+  if (e == cudaSuccess) {
+    mas_kernel<<<B, MAS_THREADS, smem, st>>>(d_value, d_path, d_ty, d_tx, Ty, Tx);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) { g_free_err = std::string("vtts_maximum_path: ") + cudaGetErrorString(e); return VTTS_ERR_CUDA; }
+  return VTTS_OK;
+}
+
+int vtts_maximum_path_dev(float* d_value, const int32_t* d_t_ys, const int32_t* d_t_xs, int B, int T_y, int T_x, int32_t* d_path, void* stream) {
+  if (!d_value || !d_t_ys || !d_t_xs || !d_path || B <= 0 || T_y <= 0 || T_x <= 0) { g_free_err = "vtts_maximum_path_dev: bad argument"; return VTTS_ERR_INVALID; }
+  return mas_launch(d_value, d_t_ys, d_t_xs, B, T_y, T_x, d_path, (cudaStream_t)stream);
+}
+
+int vtts_maximum_path(const float* neg_cent, const int32_t* t_ys, const int32_t* t_xs, int B, int T_y, int T_x, int32_t* path, int device) {
+  if (!neg_cent || !t_ys || !t_xs || !path || B <= 0 || T_y <= 0 || T_x <= 0) { g_free_err = "vtts_maximum_path: bad argument"; return VTTS_ERR_INVALID; }
+  for (int b = 0; b < B; ++b)
+    if (t_ys[b] < 0 || t_ys[b] > T_y || t_xs[b] < 0 || t_xs[b] > T_x || t_xs[b] > t_ys[b]) {
+      g_free_err = "vtts_maximum_path: lengths must satisfy 0 <= t_x <= t_y <= T_y, t_x <= T_x (utterance " + std::to_string(b) + ")";
+      return VTTS_ERR_INVALID;
+    }
+  float* dv = nullptr; int *dp = nullptr, *dl = nullptr;
+  const size_t n = (size_t)B * T_y * T_x;
+  int rc = VTTS_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&dv, n * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&dp, n * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&dl, (size_t)2 * B * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemcpy(dv, neg_cent, n * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dl, t_ys, (size_t)B * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dl + B, t_xs, (size_t)B * sizeof(int), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) rc = mas_launch(dv, dl, dl + B, B, T_y, T_x, dp, 0);
+  if (e == cudaSuccess && rc == VTTS_OK) e = cudaMemcpy(path, dp, n * sizeof(int), cudaMemcpyDeviceToHost);
+  if (dv) cudaFree(dv);
+  if (dp) cudaFree(dp);
+  if (dl) cudaFree(dl);
+  if (e != cudaSuccess) { g_free_err = std::string("vtts_maximum_path: ") + cudaGetErrorString(e); return VTTS_ERR_CUDA; }
+  return rc;
+}
 
 int vtts_durations(vtts_handle h, const int64_t* ids, const int64_t* lengths, const int64_t* sid, int B, int t_max,
                    const float* scales, const float* noise_dp, uint64_t seed, int64_t* y_lengths, int32_t* durations) {

@@ -43,7 +43,8 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_kernel_launches", "vtts_stream", "vtts_microbench", "vtts_debug_flags", "vtts_debug_read",
            "vtts_profile", "vtts_profile_read", "vtts_set_graphs", "vtts_graph_replays",
            "vtts_profile_read_tc", "vtts_timeline", "vtts_infer", "vtts_infer_dev",
-           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention", "vtts_speculation_stats", "vtts_host_timings"]
+           "vtts_decoder_halo", "vtts_flow", "vtts_decode_chunk", "vtts_debug_attention", "vtts_speculation_stats", "vtts_host_timings",
+           "vtts_maximum_path", "vtts_maximum_path_dev"]
 
 
 def lib_path():
@@ -118,6 +119,10 @@ def load_library(build_if_missing=True):
     lib.vtts_speculation_stats.restype = i32
     lib.vtts_host_timings.argtypes = [vp, C.POINTER(C.c_double), i32]
     lib.vtts_host_timings.restype = i32
+    lib.vtts_maximum_path.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+    lib.vtts_maximum_path.restype = i32
+    lib.vtts_maximum_path_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.vtts_maximum_path_dev.restype = i32
     _LIB = lib
     return lib
 
