@@ -306,7 +306,7 @@ struct vtts_engine {
   uint64_t ws_gen = 0, graph_clock = 0, graph_replays = 0;
   bool capture_on_first = true;
   bool capturing = false, use_graphs = true, last_graphed = false, use_pdl = true;    // programmatic dependent launch (VTTS_PDL=0 turns it off)
-  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, conv_big_g = 1, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 2, n_sm = 148, tc_coal = 0, tc_dbgskip = 0, tc_wmc = 0;
+  int conv_max_s = 8, conv_target = 120, conv_max_g = 4, conv_big_g = 1, tc_tall = 0, tc_baseoff = 0, tc_bn = 0, attn_rows = 0, tc_mc = 0, tc_split = 0, conv_min_g = 1, tc_min_steps = 2, conv_auto_g = 4, attn_split = 1, tc_persist = 1, tc_persist_min = 1, n_sm = 148, tc_coal = 0, tc_dbgskip = 0, tc_wmc = 0;
   int tc_cluster_cap[2][3] = {{0, 0, 0}, {0, 0, 0}};   // co-resident clusters of 2/4/8 conv_tc CTAs, [BN 64/128][log2(S)-1]   // multicast measured slower   // tuning knobs (env VTTS_CONV_MAXS / _TARGET / _MAXG)
   cudaEvent_t ev[8] = {};
   cudaStream_t side[3] = {};               // branch streams of the decoder's independent resblock chains (forked / joined with events)
@@ -876,7 +876,14 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.ast = (np == 3 || tall) ? 2 : (BN == 128 ? tc_ast<128>() : tc_ast<64>());
   // launches without split-K finish their tiles through a 32 KB transposition buffer (coalesced epilogue, conv_tc.cuh); with
   // 128-wide channel tiles it takes the place of the fourth weight stage
-  tb.coal = (split == 1 && tc_coal) ? 1 : 0;
+  long tiles_all = 0;                        // the launch's tile space (one wave or less: the one-tile-per-CTA kernel)
+  {
+    int mc = 0, ml = 0;
+    for (const TcSpec& q : ps) { mc = std::max(mc, q.Cout); ml = std::max(ml, maxLen * rmul + q.in_extra); }
+    tiles_all = (long)((ml + TC_BM - 1) / TC_BM) * ((mc + BN - 1) / BN) * nB * (long)ps.size() * split;
+  }
+  const bool one_wave = tiles_all <= 148 && !(tc_persist == 2 && split == 1 && cn == 1);
+  tb.coal = (split == 1 && !one_wave && tc_coal) ? 1 : 0;
   const int stage_bytes = tb.coal ? TC_STAGE_BYTES : 0;
   tb.wst = np == 3 ? (BN == 128 ? 2 : 3) : (BN == 128 ? (tb.coal ? 3 : tc_wst<128>()) : tc_wst<64>());
   tb.split = split;
@@ -917,12 +924,11 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
   tb.dbg = tc_dbg;
   dim3 grid((maxL + TC_BM - 1) / TC_BM, (maxCout + BN - 1) / BN, nB * tb.n * split);
   if (grid.x == 0) return;
-  tb.wpre = (long)grid.x * grid.y * grid.z <= 148 ? 1 : 0;
+  tb.wpre = one_wave ? 1 : 0;
   // machine-filling launches: one resident CTA per SM walks the tile space (conv_tc.cuh)
   tb.gx = (int)grid.x; tb.gy = (int)grid.y; tb.gz = (int)grid.z;
   tb.persist = 0;
   tb.wmc = 1;
-  if (tc_persist == 2 && split == 1 && cn == 1) tb.wpre = 0;
   if (split == 1 && cn == 1 && !tb.wpre && (tc_persist == 2 || (tc_persist && (long)grid.x * grid.y * grid.z > (long)tc_persist_min * n_sm))) {
     tb.persist = 1;
     tb.wmc = wmc;
@@ -965,9 +971,9 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     if (split > 1 || tb.wpre) {
       if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true>, tb, lens, offs));
       else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true>, tb, lens, offs));
-    } else {
-      if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, false>, tb, lens, offs));
-      else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, false>, tb, lens, offs));
+    } else {                      // more than one wave of tiles: the persistent kernel (also runs them one per CTA when tb.persist == 0)
+      if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<128>, tb, lens, offs));
+      else CK(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<64>, tb, lens, offs));
     }
   }
   CK(cudaGetLastError());
@@ -2332,8 +2338,8 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
       REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, VTTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_persist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CK(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       for (int wi = 0; wi < 2; ++wi)

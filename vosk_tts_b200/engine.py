@@ -119,10 +119,11 @@ def load_library(build_if_missing=True):
     lib.vtts_speculation_stats.restype = i32
     lib.vtts_host_timings.argtypes = [vp, C.POINTER(C.c_double), i32]
     lib.vtts_host_timings.restype = i32
-    lib.vtts_maximum_path.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
-    lib.vtts_maximum_path.restype = i32
-    lib.vtts_maximum_path_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
-    lib.vtts_maximum_path_dev.restype = i32
+    if hasattr(lib, "vtts_maximum_path") or not os.environ.get("VTTS_LIB"):      # (an older build loaded for an A/B lacks it)
+        lib.vtts_maximum_path.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+        lib.vtts_maximum_path.restype = i32
+        lib.vtts_maximum_path_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+        lib.vtts_maximum_path_dev.restype = i32
     _LIB = lib
     return lib
 
