@@ -14,7 +14,7 @@ import numpy as np, torch
 from vosk_tts_b200 import config as C, synthetic, weights
 from vosk_tts_b200.engine import Engine
 cfg = C.DEFAULT_CONFIG
-blob, man = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg, precision=1)
+blob, man = weights.pack(weights.fold_weight_norm(synthetic.make_random_checkpoint(cfg, 1234)), cfg)      # full pack: also what older builds expect
 eng = Engine(cfg, blob, man, device=0, precision=1)
 g = torch.Generator().manual_seed(0)
 tok = torch.randint(0, cfg["n_vocab"], (1, 128), generator=g)

@@ -445,11 +445,14 @@ constexpr int TC_MAXST = 4;   // barrier slots per ring
 // launches of an utterance (in-graph timeline A/B of the two builds, r2: conv_tc 918 -> 1006 us, step +6.9 %) -- a longer
 // prologue in front of the first TMA request and a larger image for a chain in which every launch starts cold.
 // ---------------------------------------------------------------------------------------------------------------------
-template <int BN, bool SPLIT>
+// DYN = false: two operand planes and the default ring depths as compile-time constants (the single-utterance launches of the
+// bench default; the run-time depths / plane count of DYN = true -- exact 3-way split, tall tiles -- cost ~0.4 us per launch
+// on this chain: r1 vs r2 timeline A/B, conv_tc 729 -> 756 us over 68 launches).
+template <int BN, bool SPLIT, bool DYN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
   constexpr int B_BYTES = BN * TC_BK * 2;
-  const int TC_AST = tb.ast, TC_WST = tb.wst, NP = tb.np;
+  const int TC_AST = DYN ? tb.ast : tc_ast<BN>(), TC_WST = DYN ? tb.wst : tc_wst<BN>(), NP = DYN ? tb.np : 2;
   PDL_LAUNCH();
   if (threadIdx.x == 0) TC_STAMP(0);
   // cluster split-K ways; blockIdx.z = (b * n + problem) * S + rank.  The non-split instantiation carries none of the

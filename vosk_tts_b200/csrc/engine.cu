@@ -969,8 +969,14 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     // single-wave launches all use the split-capable instantiation (also with split == 1): alternating between two kernel
     // images costs instruction-cache misses on every launch of a latency-bound chain
     if (split > 1 || tb.wpre) {
-      if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true>, tb, lens, offs));
-      else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true>, tb, lens, offs));
+      const bool dyn = tb.np != 2 || tb.ast != (BN == 128 ? tc_ast<128>() : tc_ast<64>()) || tb.wst != (BN == 128 ? tc_wst<128>() : tc_wst<64>());
+      if (BN == 128) {
+        if (dyn) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, true>, tb, lens, offs));
+        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, false>, tb, lens, offs));
+      } else {
+        if (dyn) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, true>, tb, lens, offs));
+        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, false>, tb, lens, offs));
+      }
     } else {                      // more than one wave of tiles: the persistent kernel (also runs them one per CTA when tb.persist == 0)
       if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<128>, tb, lens, offs));
       else CK(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<64>, tb, lens, offs));
@@ -2340,8 +2346,10 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
       h->encode_tiled = reinterpret_cast<vtts_engine::EncodeFn>(fn);
       CK(cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       CK(cudaFuncSetAttribute(conv_tc_persist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      CK(cudaFuncSetAttribute(conv_tc_kernel<128, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       for (int wi = 0; wi < 2; ++wi)
         for (int si = 0; si < 3; ++si) {
           const int S = 2 << si;
@@ -2354,7 +2362,7 @@ int vtts_create(const vtts_config* cfg, const float* blob, size_t blob_floats, c
           at[0].val.clusterDim.x = 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = S;
           lc.attrs = at; lc.numAttrs = 1;
           int nc = 0;
-          cudaError_t e = wi ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<128, true>, &lc) : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<64, true>, &lc);
+          cudaError_t e = wi ? cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<128, true, false>, &lc) : cudaOccupancyMaxActiveClusters(&nc, conv_tc_kernel<64, true, false>, &lc);
           if (e != cudaSuccess) { nc = 0; cudaGetLastError(); }
           h->tc_cluster_cap[wi][si] = nc;
         }

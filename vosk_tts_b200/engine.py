@@ -47,6 +47,29 @@ EXPORTS = ["vtts_create", "vtts_destroy", "vtts_last_error", "vtts_durations", "
            "vtts_maximum_path", "vtts_maximum_path_dev"]
 
 
+class _Missing:
+    """Stand-in for an entry point an alternative build (VTTS_LIB) does not export: accepts the argtypes / restype
+    assignments of load_library and raises when called."""
+
+    def __init__(self, name):
+        self._name = name
+
+    def __call__(self, *a):
+        raise RuntimeError("%s is not exported by the library selected with VTTS_LIB" % self._name)
+
+
+class _TolerantLib:
+    def __init__(self, lib):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_missing", {})
+
+    def __getattr__(self, name):
+        try:
+            return getattr(self._lib, name)
+        except AttributeError:
+            return self._missing.setdefault(name, _Missing(name))
+
+
 def lib_path():
     return _build.LIB
 
@@ -62,6 +85,8 @@ def load_library(build_if_missing=True):
             raise RuntimeError("libvtts.so is missing: run `python -m vosk_tts_b200.build`")
         _build.build()
     lib = C.CDLL(path)
+    if os.environ.get("VTTS_LIB"):
+        lib = _TolerantLib(lib)                 # an older build loaded for an A/B may lack the newest entry points
     vp, i32, i64p, fp = C.c_void_p, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_float)
     lib.vtts_create.argtypes = [C.POINTER(VttsConfig), vp, C.c_size_t, C.c_char_p, i32, i32, C.POINTER(vp)]
     lib.vtts_create.restype = i32
@@ -119,11 +144,10 @@ def load_library(build_if_missing=True):
     lib.vtts_speculation_stats.restype = i32
     lib.vtts_host_timings.argtypes = [vp, C.POINTER(C.c_double), i32]
     lib.vtts_host_timings.restype = i32
-    if hasattr(lib, "vtts_maximum_path") or not os.environ.get("VTTS_LIB"):      # (an older build loaded for an A/B lacks it)
-        lib.vtts_maximum_path.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
-        lib.vtts_maximum_path.restype = i32
-        lib.vtts_maximum_path_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
-        lib.vtts_maximum_path_dev.restype = i32
+    lib.vtts_maximum_path.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32]
+    lib.vtts_maximum_path.restype = i32
+    lib.vtts_maximum_path_dev.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp]
+    lib.vtts_maximum_path_dev.restype = i32
     _LIB = lib
     return lib
 
