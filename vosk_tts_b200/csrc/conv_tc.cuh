@@ -14,6 +14,7 @@
 // warps 2..5 = epilogue (tcgen05.ld -> bias/cond/activation/residual -> fp32 rows and/or split-bf16 planes for the
 // next conv).  A 4-stage mbarrier ring decouples TMA from the tensor pipe.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -43,9 +44,11 @@ constexpr int TC_MAXP = 4;
 
 enum : int { TCE_RELU = 1, TCE_GATE = 2 };
 
-struct TcProblem {
+// One conv of a grouped launch.  TcProblemBase is what the default kernels take as a parameter; TcProblem adds the tensor maps of
+// the third operand plane (exact 3-way split).  The launch descriptor is a __grid_constant__ kernel parameter: two more
+// 128-byte maps per problem are 1 KB more parameters on every launch of the 68-launch single-utterance chain.
+struct TcProblemBase {
   CUtensorMap a_hi, a_lo, w_hi, w_lo;
-  CUtensorMap a_mid, w_mid;   // third planes of the exact 3-way split (TcBatch::np == 3)
   __nv_bfloat16* p_mid;       // third output plane (or null)
   const float* bias;
   const float* cond;          // per-utterance vector added before the activation (or null)
@@ -60,9 +63,11 @@ struct TcProblem {
   int epi;
   float alpha, pl_slope;
 };
+struct TcProblem : TcProblemBase {
+  CUtensorMap a_mid, w_mid;   // third planes of the exact 3-way split (np == 3)
+};
 
-struct TcBatch {
-  TcProblem p[TC_MAXP];
+struct TcBatchScalars {
   int n;
   int rmul;
   int tall;     // 1: one activation tile of 128 + (k-1)*dil rows per channel chunk, taps address it through row-shifted
@@ -85,6 +90,20 @@ struct TcBatch {
                 //    64/split of the tile's columns (reduce-scatter; fixed summation order => deterministic).  1 = off
   unsigned long long* dbg;   // optional: %globaltimer stamps of CTA (0,0,0) for tuning (tools/microbench.py)
 };
+template <class PT, int MP = TC_MAXP>
+struct TcBatchT : TcBatchScalars {
+  PT p[MP];
+};
+using TcBatch = TcBatchT<TcProblem>;          // what the host fills
+// Parameter of the two-plane one-tile kernels: no third-plane maps (3.7 KB -> 2.65 KB of kernel parameters: conv_tc 744 -> 723 us
+// over the 68 launches of an utterance, in-graph A/B).
+template <int MP>
+inline TcBatchT<TcProblemBase, MP> tc_lite(const TcBatch& tb) {
+  TcBatchT<TcProblemBase, MP> l;
+  static_cast<TcBatchScalars&>(l) = tb;
+  for (int i = 0; i < MP; ++i) l.p[i] = tb.p[i];               // (slices the third-plane maps off)
+  return l;
+}
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -162,7 +181,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 
 // ---- epilogue pieces shared by the plain and the split-K paths: EN accumulator columns starting at absolute column `cofs`
 template <int EN>
-__device__ __forceinline__ void tc_load_res(const TcProblem& P, float (&rr)[EN], int cofs, long orow, bool rowok) {
+__device__ __forceinline__ void tc_load_res(const TcProblemBase& P, float (&rr)[EN], int cofs, long orow, bool rowok) {
   const bool gate = (P.epi & TCE_GATE) != 0;
   const int ocb = gate ? (cofs >> 1) : cofs;
   const int nvalid = gate ? min(EN / 2, (P.Cout >> 1) - ocb) : min(EN, P.Cout - cofs);
@@ -185,7 +204,7 @@ __device__ __forceinline__ void tc_load_res(const TcProblem& P, float (&rr)[EN],
 }
 // v = accumulator + bias of EN columns; applies gate / relu / alpha / residual and stores fp32 rows and split-bf16 planes
 template <int EN>
-__device__ __forceinline__ void tc_finish_cols(const TcProblem& P, float (&v)[EN], const float (&rr)[EN], int cofs, long orow) {
+__device__ __forceinline__ void tc_finish_cols(const TcProblemBase& P, float (&v)[EN], const float (&rr)[EN], int cofs, long orow) {
   const bool gate = (P.epi & TCE_GATE) != 0;
   const bool relu = (P.epi & TCE_RELU) != 0;
   const int ocb = gate ? (cofs >> 1) : cofs;           // first output channel of this pass
@@ -263,7 +282,7 @@ __device__ __forceinline__ void tc_finish_cols(const TcProblem& P, float (&v)[EN
 // reads it back with 16 lanes per row: a warp instruction then covers two rows x 256 contiguous bytes, the residual
 // is loaded and the fp32 rows / bf16 planes are stored as full lines.  `stg` = this warp's [32][64] floats.
 template <bool GATE>
-__device__ __forceinline__ void tc_finish_rows(const TcProblem& P, const float* stg, const float* bias_t, int cofs, int trow0, int L,
+__device__ __forceinline__ void tc_finish_rows(const TcProblemBase& P, const float* stg, const float* bias_t, int cofs, int trow0, int L,
                                                long out_base, int lane, const float4 (&rq)[16], bool r_pre) {
   constexpr int NO = GATE ? 2 : 4;                    // outputs per thread (a gate pair (2i, 2i+1) makes one channel)
   const int half = lane >> 4, cj = lane & 15;
@@ -355,7 +374,7 @@ __device__ __forceinline__ void tc_finish_rows(const TcProblem& P, const float* 
 
 // residual of the 16 (row, 4-column) units tc_finish_rows<false> handles in this thread, requested in one go (the loads
 // are in flight while the mainloop of the tile still runs).  Returns false when the vector path does not apply.
-__device__ __forceinline__ bool tc_prefetch_res_rows(const TcProblem& P, float4 (&rq)[16], int cofs, int trow0, int L, long out_base, int lane) {
+__device__ __forceinline__ bool tc_prefetch_res_rows(const TcProblemBase& P, float4 (&rq)[16], int cofs, int trow0, int L, long out_base, int lane) {
   if (!P.res || (P.epi & TCE_GATE) || ((P.ldr | P.roff) & 3) != 0) return false;
   const int half = lane >> 4, cj = lane & 15;
   const int c = cofs + cj * 4;
@@ -394,7 +413,7 @@ __device__ __forceinline__ void tc_split_send(const float (&acc)[64], int half, 
   }
 }
 template <int SS, int BN>
-__device__ __forceinline__ void tc_split_finish(const TcProblem& P, const float* stage, const float* bias_s, int sp, int row, int co0,
+__device__ __forceinline__ void tc_split_finish(const TcProblemBase& P, const float* stage, const float* bias_s, int sp, int row, int co0,
                                                 long orow, bool rowok) {
   constexpr int W = BN / SS;
   float rr[W];
@@ -417,7 +436,7 @@ __device__ __forceinline__ void tc_split_finish(const TcProblem& P, const float*
   if (rowok && co0 + sp * W < P.Cout) tc_finish_cols<W>(P, v, rr, co0 + sp * W, orow);
 }
 template <int SS, int BN, typename LoadAcc>
-__device__ __forceinline__ void tc_split_tail(const TcProblem& P, LoadAcc&& load_acc, float* stage, const float* bias_s, int sp, int row,
+__device__ __forceinline__ void tc_split_tail(const TcProblemBase& P, LoadAcc&& load_acc, float* stage, const float* bias_s, int sp, int row,
                                               int co0, long orow, bool rowok) {
   float v[64];
   load_acc(0, v);
@@ -448,9 +467,10 @@ constexpr int TC_MAXST = 4;   // barrier slots per ring
 // DYN = false: two operand planes and the default ring depths as compile-time constants (the single-utterance launches of the
 // bench default; the run-time depths / plane count of DYN = true -- exact 3-way split, tall tiles -- cost ~0.4 us per launch
 // on this chain: r1 vs r2 timeline A/B, conv_tc 729 -> 756 us over 68 launches).
-template <int BN, bool SPLIT, bool DYN>
+template <int BN, bool SPLIT, bool DYN, int MP = TC_MAXP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens, const int* __restrict__ offs) {
+conv_tc_kernel(const __grid_constant__ TcBatchT<std::conditional_t<DYN, TcProblem, TcProblemBase>, MP> tb, const int* __restrict__ lens,
+               const int* __restrict__ offs) {
   constexpr int B_BYTES = BN * TC_BK * 2;
   const int TC_AST = DYN ? tb.ast : tc_ast<BN>(), TC_WST = DYN ? tb.wst : tc_wst<BN>(), NP = DYN ? tb.np : 2;
   PDL_LAUNCH();
@@ -461,7 +481,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
   const int zi = blockIdx.z / S, sp = blockIdx.z - zi * S;
   const int pi = zi % tb.n;
   const int b = zi / tb.n;
-  const TcProblem& P = tb.p[pi];
+  const auto& P = tb.p[pi];
   const int co0 = blockIdx.y * BN;
   if (co0 >= P.Cout) return;
   const int t0 = blockIdx.x * TC_BM;
@@ -493,9 +513,11 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_lo)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_lo)) : "memory");
-    if (NP == 3) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_mid)) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_mid)) : "memory");
+    if constexpr (DYN) {
+      if (NP == 3) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.a_mid)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&P.w_mid)) : "memory");
+      }
     }
   }
   if (warp == 1) {
@@ -523,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
     mbar_expect_tx(&w_full[wst], NP * B_BYTES);
     tma_load_2d(wb, &P.w_hi, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
     tma_load_2d(wb + B_BYTES, &P.w_lo, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
-    if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]);
+    if constexpr (DYN) { if (NP == 3) tma_load_2d(wb + 2 * B_BYTES, &P.w_mid, c * TC_BK, j * P.Cout + co0, &w_full[wst]); }
   };
   if (warp == 0 && lane == 0) {
     int c = s_beg / P.k, j = s_beg - c * P.k;
@@ -567,7 +589,7 @@ conv_tc_kernel(const __grid_constant__ TcBatch tb, const int* __restrict__ lens,
           } else {
             tma_load_2d(ab, &P.a_hi, c * TC_BK, row, &a_full[ast]);
             tma_load_2d(ab + A_BYTES, &P.a_lo, c * TC_BK, row, &a_full[ast]);
-            if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]);
+            if constexpr (DYN) { if (NP == 3) tma_load_2d(ab + 2 * A_BYTES, &P.a_mid, c * TC_BK, row, &a_full[ast]); }
           }
           if (++ast == TC_AST) { ast = 0; ++a_use; }
         }

@@ -970,12 +970,15 @@ void vtts_engine::launch_tc(const std::vector<TcSpec>& ps, int rmul, const int* 
     // images costs instruction-cache misses on every launch of a latency-bound chain
     if (split > 1 || tb.wpre) {
       const bool dyn = tb.np != 2 || tb.ast != (BN == 128 ? tc_ast<128>() : tc_ast<64>()) || tb.wst != (BN == 128 ? tc_wst<128>() : tc_wst<64>());
-      if (BN == 128) {
-        if (dyn) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, true>, tb, lens, offs));
-        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, false>, tb, lens, offs));
-      } else {
-        if (dyn) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, true>, tb, lens, offs));
-        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, false>, tb, lens, offs));
+      if (dyn) {
+        if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, true>, tb, lens, offs));
+        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, true>, tb, lens, offs));
+      } else {                    // the default launches carry the descriptor without the third-plane tensor maps
+        // (a one-slot descriptor for the single-conv launches was tried as well: alternating between two kernel images on the
+        //  chain cost more than the 2 KB of parameters saved -- conv_tc 723 -> 765 us in-graph)
+        const auto tl = tc_lite<TC_MAXP>(tb);
+        if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<128, true, false, TC_MAXP>, tl, lens, offs));
+        else CK(cudaLaunchKernelEx(&lc, conv_tc_kernel<64, true, false, TC_MAXP>, tl, lens, offs));
       }
     } else {                      // more than one wave of tiles: the persistent kernel (also runs them one per CTA when tb.persist == 0)
       if (BN == 128) CK(cudaLaunchKernelEx(&lc, conv_tc_persist_kernel<128>, tb, lens, offs));
