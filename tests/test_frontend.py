@@ -86,3 +86,48 @@ def test_g2p_matches_reference_converter():
         words.append(w[:p] + "+" + w[p:])
     for w in words:
         assert g2p.convert(w) == ref.convert(w), w
+
+
+class _StubEngine:
+    hop = 256
+
+    def __init__(self):
+        self.calls = []
+
+    def synthesize_stream(self, ids, sid, scales, chunk_frames=64, noise_dp=None, noise_z=None, seed=0):
+        self.calls.append((ids.copy(), sid, np.array(scales), chunk_frames, seed))
+        frames = 3 * ids.shape[1]
+        for f0 in range(0, frames, chunk_frames):
+            n = (min(frames, f0 + chunk_frames) - f0) * self.hop
+            yield np.full(n, 0.5, np.float32)
+
+
+def test_streaming_front_end_chunks_lock_and_lengths(tmp_path):
+    """Synth.synth_audio_stream -> VitsSession.run_stream -> Engine.synthesize_stream: same feeds as synth_audio, int16 chunks,
+    the session lock is held while a stream is open and released when it ends or is abandoned."""
+    import threading
+    from vosk_tts_b200.session import VitsSession
+    sess = VitsSession.__new__(VitsSession)
+    sess.cfg, sess.engine, sess._lock, sess._seed, sess._calls = {}, _StubEngine(), threading.Lock(), 7, 0
+    sess.last_y_lengths = sess.last_wav_lengths = None
+    m = Model(model_path=_model_dir(tmp_path), session=sess)
+    s = Synth(m)
+    ids = s.g2p_noembed("Привет, мир")
+    chunks = list(s.synth_audio_stream("Привет, мир", speaker_id=3, chunk_frames=10))
+    frames = 3 * len(ids)
+    assert len(chunks) == -(-frames // 10) and all(c.dtype == np.int16 for c in chunks)
+    assert sum(c.size for c in chunks) == frames * 256 and int(chunks[0][0]) == int(0.5 * 32767)
+    got_ids, sid, scales, cf, seed = sess.engine.calls[-1]
+    assert got_ids.tolist() == [ids] and sid == 3 and cf == 10 and np.allclose(scales, [0.7, 1 / 1.25, 0.8])
+    assert list(sess.last_wav_lengths) == [frames * 256] and list(sess.last_y_lengths) == [frames]
+    assert not sess._lock.locked()
+    gen = s.synth_audio_stream("Привет", speaker_id=0, chunk_frames=4)
+    next(gen)
+    assert sess._lock.locked()                      # a second request would wait here until the stream is finished
+    gen.close()
+    assert not sess._lock.locked()
+    # two consecutive streams draw different seeds (per-call Philox seed, like run())
+    list(s.synth_audio_stream("Привет", chunk_frames=64))
+    assert sess.engine.calls[-1][4] != sess.engine.calls[-2][4]
+    with pytest.raises(ValueError):
+        list(sess.run_stream({"input": np.zeros((2, 3), np.int64), "input_lengths": np.array([3, 3]), "scales": np.ones(3, np.float32)}))

@@ -142,3 +142,43 @@ def test_real_engine_behind_the_service(tmp_path):
         assert len(b"".join(res[2])) > len(b"".join(res[0]))
     finally:
         srv.stop(0)
+
+
+class _LockingStub(_StubSynth):
+    """Holds a lock for the duration of a stream, like VitsSession.run_stream holds the session lock."""
+
+    def __init__(self):
+        super().__init__()
+        self.engine_lock = threading.Lock()
+
+    def synth_audio_stream(self, text, speaker_id=0, speech_rate=1.0, chunk_frames=64):
+        with self.engine_lock:
+            pcm = self._pcm(text, speaker_id, speech_rate)
+            for i in range(0, len(pcm), 256 * chunk_frames):
+                yield pcm[i:i + 256 * chunk_frames]
+
+
+def test_cancelled_stream_releases_the_engine():
+    """A client that goes away in the middle of a stream must not leave the (single, shared) engine locked: the servicer closes
+    the generator chain, the next request is served."""
+    import time
+    stub = _LockingStub()
+    srv, port = S.make_server(stub, "127.0.0.1:0", threads=2, chunk_frames=1)
+    srv.start()
+    try:
+        addr = "127.0.0.1:%d" % port
+        M = S.messages()
+        with grpc.insecure_channel(addr) as channel:
+            call = channel.unary_stream("/%s/%s" % (S.SERVICE, S.METHOD), request_serializer=lambda m: m.SerializeToString(),
+                                        response_deserializer=M["UtteranceSynthesisResponse"].FromString)
+            it = call(M["UtteranceSynthesisRequest"](text="a long utterance that will be abandoned " * 20))
+            first = next(it)
+            assert len(first.audio_chunk.data) == 512
+            it.cancel()
+        t0 = time.time()
+        while stub.engine_lock.locked() and time.time() - t0 < 10:
+            time.sleep(0.05)
+        assert not stub.engine_lock.locked(), "the abandoned stream still holds the engine"
+        assert b"".join(S.synthesize(addr, "next request", speaker_id=1, timeout=10))
+    finally:
+        srv.stop(0)

@@ -125,9 +125,13 @@ class SynthesizerServicer:
             context.abort(grpc.StatusCode.INVALID_ARGUMENT, "speech_rate must be positive")
         try:
             if self.chunk_frames > 0 and hasattr(self.synth, "synth_audio_stream"):
-                for pcm in self.synth.synth_audio_stream(request.text, speaker_id=speaker_id, speech_rate=speech_rate,
-                                                         chunk_frames=self.chunk_frames):
-                    yield M["UtteranceSynthesisResponse"](audio_chunk=M["AudioChunk"](data=pcm.tobytes()))
+                stream = self.synth.synth_audio_stream(request.text, speaker_id=speaker_id, speech_rate=speech_rate,
+                                                       chunk_frames=self.chunk_frames)
+                try:
+                    for pcm in stream:
+                        yield M["UtteranceSynthesisResponse"](audio_chunk=M["AudioChunk"](data=pcm.tobytes()))
+                finally:
+                    stream.close()      # a cancelled RPC must not leave the engine locked for the next request
             else:
                 audio = self.synth.synth_audio(request.text, speaker_id=speaker_id, speech_rate=speech_rate)
                 yield M["UtteranceSynthesisResponse"](audio_chunk=M["AudioChunk"](data=audio.tobytes()))

@@ -96,9 +96,15 @@ class VitsSession:
             self._calls += 1
             seed = (self._seed * 0x9E3779B97F4A7C15 + self._calls) & 0xFFFFFFFFFFFFFFFF
             total = 0
-            for chunk in self.engine.synthesize_stream(ids[:, :n], sid, scales, chunk_frames=chunk_frames, seed=seed):
-                total += chunk.size
-                yield chunk
+            stream = self.engine.synthesize_stream(ids[:, :n], sid, scales, chunk_frames=chunk_frames, seed=seed)
+            try:
+                for chunk in stream:
+                    total += chunk.size
+                    yield chunk
+            finally:
+                # closing THIS generator does not finalise a generator it iterates over (the frame keeps it alive): close it
+                # explicitly so that an abandoned stream (client gone) ends here and the lock below is released now
+                stream.close()
             self.last_wav_lengths = np.array([total], np.int64)
             self.last_y_lengths = self.last_wav_lengths // self.engine.hop
 

@@ -91,9 +91,13 @@ class Synth:
                  "bert": None, "phone_duration_extra": None}
         t0 = time.perf_counter()
         n = 0
-        for chunk in self.model.onnx.run_stream(feeds, chunk_frames=chunk_frames):
-            n += chunk.size
-            yield self.audio_float_to_int16(chunk * scale)
+        stream = self.model.onnx.run_stream(feeds, chunk_frames=chunk_frames)
+        try:
+            for chunk in stream:
+                n += chunk.size
+                yield self.audio_float_to_int16(chunk * scale)
+        finally:
+            stream.close()              # releases the session (its lock) also when the consumer abandons this generator
         infer_sec = time.perf_counter() - t0
         dur = n / 22050
         logging.info("Real-time factor: %0.2f (infer=%0.2f sec, audio=%0.2f sec)" % (infer_sec / dur if dur > 0 else 0.0, infer_sec, dur))
